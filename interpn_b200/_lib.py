@@ -11,7 +11,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libinterpn_b200.so")
+# INTERPN_B200_LIBRARY selects another build of the same library (kernel-tuning experiments only).
+LIB_PATH = os.environ.get("INTERPN_B200_LIBRARY") or os.path.join(_HERE, "libinterpn_b200.so")
 
 # Status codes of include/interpn_b200.h
 OK = 0
@@ -48,6 +49,7 @@ def _load() -> C.CDLL:
     for name in ("interpn_b200_interp_vals_len", "interpn_b200_interp_elem_size", "interpn_b200_interp_ndims"):
         getattr(lib, name).restype = C.c_size_t
         getattr(lib, name).argtypes = [C.c_void_p]
+    lib.interpn_b200_interp_vals_updated.argtypes = [C.c_void_p, C.c_void_p]
     lib.interpn_b200_interp_free.restype = None
     lib.interpn_b200_interp_free.argtypes = [C.c_void_p]
     lib.interpn_b200_interp_status.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]

@@ -9,6 +9,7 @@
 #include <atomic>
 #include <climits>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -258,13 +259,34 @@ int validate_interp(size_t ndims, const size_t* obs_lens, size_t nobs, size_t no
     return INTERPN_B200_OK;
 }
 
+// Which grids get the window layout (kernels.cuh load_row). It multiplies the footprint by W, so it is
+// reserved for grids that are too big for L1 to capture row reuse, yet whose W-fold copy still sits
+// comfortably inside the 126 MB L2 next to the streaming query traffic. INTERPN_B200_WINDOW_MB overrides
+// the upper bound (0 disables the layout).
+int window_width(const DeviceGrid& g) {
+    int w = 0;
+    if (g.method == INTERPN_B200_LINEAR && g.ndims <= 6) w = 2;
+    if (g.method == INTERPN_B200_CUBIC && g.ndims <= 4) w = 4;
+    if (!w) return 0;
+    size_t max_mb = 64;
+    if (const char* e = getenv("INTERPN_B200_WINDOW_MB")) max_mb = static_cast<size_t>(strtoull(e, nullptr, 10));
+    const size_t bytes = g.nvals * static_cast<size_t>(g.elem);
+    if (bytes < (size_t(128) << 10) || bytes * w > (max_mb << 20)) return 0;
+    return w;
+}
+
 int upload_vals(interpn_b200_interp* h, const void* vals, int vals_location) {
-    const size_t bytes = h->g.nvals * static_cast<size_t>(h->g.elem);
-    CUDA_TRY(cudaMalloc(&h->g.vals, bytes ? bytes : 1));
+    DeviceGrid& g = h->g;
+    const size_t bytes = g.nvals * static_cast<size_t>(g.elem);
+    CUDA_TRY(cudaMalloc(&g.vals, bytes ? bytes : 1));
+    g.win_width = window_width(g);
+    if (g.win_width) CUDA_TRY(cudaMalloc(&g.win, bytes * g.win_width));
     if (vals_location == INTERPN_B200_VALS_UNINIT) return INTERPN_B200_OK;
     if (!vals) return INTERPN_B200_ERR_INVALID_ARG;
-    CUDA_TRY(cudaMemcpy(h->g.vals, vals, bytes,
+    CUDA_TRY(cudaMemcpy(g.vals, vals, bytes,
                         vals_location == INTERPN_B200_VALS_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    CUDA_TRY(launch_build_window(g, nullptr));
+    CUDA_TRY(cudaStreamSynchronize(nullptr));
     return INTERPN_B200_OK;
 }
 
@@ -740,6 +762,12 @@ int interpn_b200_interp_status(interpn_b200_interp* interp, void* stream, size_t
 }
 
 void* interpn_b200_interp_vals_ptr(interpn_b200_interp* interp) { return interp ? interp->g.vals : nullptr; }
+
+int interpn_b200_interp_vals_updated(interpn_b200_interp* interp, void* stream) {
+    if (!interp) return INTERPN_B200_ERR_INVALID_ARG;
+    CUDA_TRY(launch_build_window(interp->g, static_cast<cudaStream_t>(stream)));
+    return INTERPN_B200_OK;
+}
 size_t interpn_b200_interp_vals_len(const interpn_b200_interp* interp) { return interp ? interp->g.nvals : 0; }
 size_t interpn_b200_interp_elem_size(const interpn_b200_interp* interp) { return interp ? interp->g.elem : 0; }
 size_t interpn_b200_interp_ndims(const interpn_b200_interp* interp) { return interp ? interp->g.ndims : 0; }
@@ -747,6 +775,7 @@ size_t interpn_b200_interp_ndims(const interpn_b200_interp* interp) { return int
 void interpn_b200_interp_free(interpn_b200_interp* interp) {
     if (!interp) return;
     if (interp->g.vals) cudaFree(interp->g.vals);
+    if (interp->g.win) cudaFree(interp->g.win);
     if (interp->g.axes) cudaFree(interp->g.axes);
     if (interp->first_bad_dev) cudaFree(interp->first_bad_dev);
     delete interp;

@@ -22,6 +22,10 @@ struct DeviceGrid {
     double step[kMaxNd] = {};
     void* vals = nullptr;           // device, nvals elements
     size_t nvals = 0;
+    // Window layout of `vals` (kernels.cuh load_row): win[f*W + j] = vals[min(f + j, nvals-1)], W = 2
+    // (linear) or 4 (cubic). Present only for mid-size grids (window_policy in capi.cu).
+    void* win = nullptr;
+    int win_width = 0;
     void* axes = nullptr;           // device, all rectilinear axes packed back to back
     int axis_off[kMaxNd] = {};      // element offset of axis d inside `axes`
     int axes_total = 0;
@@ -43,6 +47,9 @@ cudaError_t launch_one_dim(int kind, bool rect, T start, T step, const T* grid, 
 // check_bounds kernel for one axis: ORs a violation flag into *flag (device int).
 template <class T>
 cudaError_t launch_check_bounds(const T* x, size_t n, T lo, T hi, T atol, int* flag, cudaStream_t stream);
+
+// Fills g.win from g.vals (stream-ordered).
+cudaError_t launch_build_window(const DeviceGrid& g, cudaStream_t stream);
 
 void count_launch();
 

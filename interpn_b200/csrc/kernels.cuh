@@ -18,10 +18,13 @@ struct EvalArgs {
     T* out;
     unsigned long long n;
     const T* vals;
+    const T* win;  // window layout of vals (see load_row), or nullptr
     long long stride[N];
     int dim[N];
     T start[N];  // regular
     T step[N];   // regular
+    T rstep[N];  // regular: RN(1/step), for exact_div
+    int fast_div;  // regular: every step is within exact_div's exponent range
     const T* axes;    // rectilinear: packed axes (global)
     int axis_off[N];  // rectilinear
     int axes_total;   // rectilinear
@@ -49,58 +52,224 @@ __device__ __forceinline__ void report_bad(unsigned long long* first_bad, unsign
 }
 
 // ---------------------------------------------------------------------------------------------
-// Multilinear (ref: multilinear/regular.rs:296-404, multilinear/rectilinear.rs:244-346)
+// Row gathers. The last grid dimension is contiguous, so every footprint (2^N / 4^N corners) is a
+// set of rows of W = 2 / 4 consecutive values. Mid-size grids additionally keep a *window layout*
+// in HBM/L2: win[f*W + j] = vals[f + j], i.e. the row starting at ANY flat index f is one naturally
+// aligned W*sizeof(T) vector — one 32-byte sector, one LDG.256/LDG.128 — instead of W scalar loads
+// that straddle two sectors 75 % (W=4) of the time.
 // ---------------------------------------------------------------------------------------------
 
-template <int D, class T, int N>
-__device__ __forceinline__ T linear_tree(const T* __restrict__ p, const long long (&stride)[N], const T (&t)[N]) {
-    using O = Ops<T>;
-    if constexpr (D == 0) {
-        return __ldg(p);
+template <class T, int W, bool WIN>
+__device__ __forceinline__ void load_row(const T* __restrict__ vals, const T* __restrict__ win, long long idx,
+                                         T (&r)[W]) {
+    if constexpr (!WIN) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) r[j] = __ldg(vals + idx + j);
+    } else if constexpr (sizeof(T) == 8 && W == 4) {
+        asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+            : "=d"(r[0]), "=d"(r[1]), "=d"(r[2]), "=d"(r[3])
+            : "l"(win + idx * 4));
+    } else if constexpr (sizeof(T) == 8 && W == 2) {
+        double2 q = __ldg(reinterpret_cast<const double2*>(win) + idx);
+        r[0] = q.x; r[1] = q.y;
+    } else if constexpr (sizeof(T) == 4 && W == 4) {
+        float4 q = __ldg(reinterpret_cast<const float4*>(win) + idx);
+        r[0] = q.x; r[1] = q.y; r[2] = q.z; r[3] = q.w;
     } else {
-        // Reduce dimension D-1 over the two sub-trees; dimension 0 is innermost, N-1 outermost.
-        T y0 = linear_tree<D - 1, T, N>(p, stride, t);
-        T y1 = linear_tree<D - 1, T, N>(p + stride[D - 1], stride, t);
-        T dy = O::sub(y1, y0);
-        return O::add(y0, O::mul(t[D - 1], dy));
+        float2 q = __ldg(reinterpret_cast<const float2*>(win) + idx);
+        r[0] = q.x; r[1] = q.y;
     }
 }
 
+// Query coordinates and results are touched exactly once: streaming loads/stores (evict-first) keep
+// them from displacing the grid in L1/L2.
+template <class T>
+__device__ __forceinline__ T load_query(const T* p) { return __ldcs(p); }
+template <class T>
+__device__ __forceinline__ void store_result(T* p, T v) { __stcs(p, v); }
+
+// P consecutive coordinates / results as one vector access (p must be P*sizeof(T)-aligned).
+template <class T, int P>
+__device__ __forceinline__ void load_query_vec(const T* p, T (&v)[P]) {
+    if constexpr (P == 1) {
+        v[0] = __ldcs(p);
+    } else if constexpr (sizeof(T) == 8 && P == 2) {
+        double2 q = __ldcs(reinterpret_cast<const double2*>(p));
+        v[0] = q.x; v[1] = q.y;
+    } else if constexpr (sizeof(T) == 8 && P == 4) {
+        asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+    } else if constexpr (sizeof(T) == 4 && P == 2) {
+        float2 q = __ldcs(reinterpret_cast<const float2*>(p));
+        v[0] = q.x; v[1] = q.y;
+    } else {
+        static_assert(sizeof(T) == 4 && P == 4, "unsupported points-per-thread");
+        float4 q = __ldcs(reinterpret_cast<const float4*>(p));
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    }
+}
+template <class T, int P>
+__device__ __forceinline__ void store_result_vec(T* p, const T (&v)[P]) {
+    if constexpr (P == 1) {
+        __stcs(p, v[0]);
+    } else if constexpr (sizeof(T) == 8 && P == 2) {
+        __stcs(reinterpret_cast<double2*>(p), make_double2(v[0], v[1]));
+    } else if constexpr (sizeof(T) == 8 && P == 4) {
+        asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+    } else if constexpr (sizeof(T) == 4 && P == 2) {
+        __stcs(reinterpret_cast<float2*>(p), make_float2(v[0], v[1]));
+    } else {
+        __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multilinear (ref: multilinear/regular.rs:296-404, multilinear/rectilinear.rs:244-346)
+// ---------------------------------------------------------------------------------------------
+
+// Reduces dimensions 0..D-1 of the sub-block at flat index `idx` for both positions of the last
+// (contiguous) dimension at once. Each lerp is the reference's `y0 + t*(y1 - y0)` with dimension 0
+// innermost, so every output is bit-identical to the reference's tree; only the load schedule differs.
+template <int D, class T, int N, bool WIN>
+__device__ __forceinline__ void linear_rows(const T* __restrict__ vals, const T* __restrict__ win, long long idx,
+                                            const long long (&stride)[N], const T (&t)[N], T (&out)[2]) {
+    using O = Ops<T>;
+    if constexpr (D == 0) {
+        load_row<T, 2, WIN>(vals, win, idx, out);
+    } else {
+        T lo[2], hi[2];
+        linear_rows<D - 1, T, N, WIN>(vals, win, idx, stride, t, lo);
+        linear_rows<D - 1, T, N, WIN>(vals, win, idx + stride[D - 1], stride, t, hi);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) out[j] = O::add(lo[j], O::mul(t[D - 1], O::sub(hi[j], lo[j])));
+    }
+}
+
+// Locate one query point: per-dimension cell origin -> flat index of the footprint's first corner,
+// and the normalized coordinates t. Returns false for an unrepresentable coordinate (regular grids).
 template <class T, int N, bool RECT>
+__device__ __forceinline__ bool linear_locate(const EvalArgs<T, N>& a, const T* __restrict__ axes, const T (&xs)[N],
+                                              T (&t)[N], long long& base) {
+    using O = Ops<T>;
+    bool ok = true;
+    base = 0;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+        const T x = xs[d];
+        int origin;
+        if constexpr (RECT) {
+            const T* g = axes + a.axis_off[d];
+            origin = clamp_cell(lower_bound(g, a.dim[d], x) - 1, a.dim[d] - 2);
+            T x0 = g[origin];
+            T x1 = g[origin + 1];
+            t[d] = O::div(O::sub(x, x0), O::sub(x1, x0));
+        } else {
+            int iloc = 0;
+            ok = floor_cell(x, a.start[d], a.step[d], a.rstep[d], a.fast_div != 0, iloc) && ok;
+            origin = clamp_cell(iloc, a.dim[d] - 2);
+            T x0 = O::add(a.start[d], O::mul(a.step[d], O::from_int(origin)));
+            t[d] = exact_div(O::sub(x, x0), a.step[d], a.rstep[d], a.fast_div != 0);
+        }
+        base += static_cast<long long>(origin) * a.stride[d];
+    }
+    return ok;
+}
+
+// Nearest: flat index of the chosen node (ref: nearest/regular.rs:259-293, nearest/rectilinear.rs:213-239).
+template <class T, int N, bool RECT>
+__device__ __forceinline__ bool nearest_locate(const EvalArgs<T, N>& a, const T* __restrict__ axes, const T (&xs)[N],
+                                               long long& idx) {
+    using O = Ops<T>;
+    const T half = T(0.5);
+    bool ok = true;
+    idx = 0;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+        const T x = xs[d];
+        int origin;
+        T dt;
+        if constexpr (RECT) {
+            const T* g = axes + a.axis_off[d];
+            origin = clamp_cell(lower_bound(g, a.dim[d], x) - 1, a.dim[d] - 2);
+            T x0 = g[origin];
+            T x1 = g[origin + 1];
+            dt = O::div(O::sub(x, x0), O::sub(x1, x0));
+        } else {
+            int iloc = 0;
+            ok = floor_cell(x, a.start[d], a.step[d], a.rstep[d], a.fast_div != 0, iloc) && ok;
+            origin = clamp_cell(iloc, a.dim[d] - 2);
+            T x0 = O::add(a.start[d], O::mul(a.step[d], O::from_int(origin)));
+            dt = exact_div(O::sub(x, x0), a.step[d], a.rstep[d], a.fast_div != 0);
+        }
+        const int off = (dt <= half) ? 0 : 1;  // tie -> lower index; NaN (rectilinear only) -> upper
+        idx += static_cast<long long>(origin + off) * a.stride[d];
+    }
+    return ok;
+}
+
+// The streaming kernels (multilinear, nearest) are a chain  DRAM load -> locate -> gather -> store
+// per point; with one point per thread the SM runs out of warps long before HBM runs out of
+// bandwidth. Each thread therefore owns P consecutive points: one 16/32-byte vector load per
+// coordinate array, P independent locate/gather chains in flight, one vector store. The host picks
+// P > 1 only when every coordinate array and `out` are P*sizeof(T)-aligned (launch_common.cuh); the
+// n % P tail is evaluated one point per thread.
+template <class T, int N, bool RECT, bool WIN, int P>
 __global__ void __launch_bounds__(kBlock) linear_kernel(const __grid_constant__ EvalArgs<T, N> a) {
     using O = Ops<T>;
     const T* axes = nullptr;
     if constexpr (RECT) axes = stage_axes<T, N>(a);
     const unsigned long long gstride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
-    for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n;
-         i += gstride) {
-        T t[N];
-        long long base = 0;
-        bool ok = true;
+    const unsigned long long gtid = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const unsigned long long ngroups = a.n / P;
+    for (unsigned long long g = gtid; g < ngroups; g += gstride) {
+        const unsigned long long i0 = g * P;
+        T xs[P][N];
 #pragma unroll
         for (int d = 0; d < N; ++d) {
-            T x = a.obs[d][i];
-            int origin;
-            if constexpr (RECT) {
-                const T* g = axes + a.axis_off[d];
-                origin = clamp_cell(static_cast<long long>(lower_bound(g, a.dim[d], x)) - 1, a.dim[d] - 2);
-                T x0 = g[origin];
-                T x1 = g[origin + 1];
-                t[d] = O::div(O::sub(x, x0), O::sub(x1, x0));
-            } else {
-                long long iloc = 0;
-                ok = floor_cell(x, a.start[d], a.step[d], iloc) && ok;
-                origin = clamp_cell(iloc, a.dim[d] - 2);
-                T x0 = O::add(a.start[d], O::mul(a.step[d], O::from_int(origin)));
-                t[d] = O::div(O::sub(x, x0), a.step[d]);
+            T v[P];
+            load_query_vec<T, P>(a.obs[d] + i0, v);
+#pragma unroll
+            for (int p = 0; p < P; ++p) xs[p][d] = v[p];
+        }
+        T res[P];
+        bool ok[P];
+        bool all_ok = true;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            T t[N];
+            long long base;
+            ok[p] = linear_locate<T, N, RECT>(a, axes, xs[p], t, base);
+            all_ok = all_ok && ok[p];
+            if (!ok[p]) base = 0;  // keep the gather in range; the value is discarded
+            T r[2];
+            linear_rows<N - 1, T, N, WIN>(a.vals, a.win, base, a.stride, t, r);
+            res[p] = O::add(r[0], O::mul(t[N - 1], O::sub(r[1], r[0])));
+        }
+        if (all_ok) {
+            store_result_vec<T, P>(a.out + i0, res);
+        } else {
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                if (ok[p]) store_result(a.out + i0 + p, res[p]);
+                else report_bad(a.first_bad, a.index_base + i0 + p);
             }
-            base += static_cast<long long>(origin) * a.stride[d];
         }
-        if (!ok) {
-            report_bad(a.first_bad, a.index_base + i);
-            continue;
+    }
+    if constexpr (P > 1) {
+        const unsigned long long i = ngroups * P + gtid;
+        if (i < a.n) {
+            T xs[N];
+#pragma unroll
+            for (int d = 0; d < N; ++d) xs[d] = load_query(a.obs[d] + i);
+            T t[N];
+            long long base;
+            if (linear_locate<T, N, RECT>(a, axes, xs, t, base)) {
+                T r[2];
+                linear_rows<N - 1, T, N, WIN>(a.vals, a.win, base, a.stride, t, r);
+                store_result(a.out + i, O::add(r[0], O::mul(t[N - 1], O::sub(r[1], r[0]))));
+            } else {
+                report_bad(a.first_bad, a.index_base + i);
+            }
         }
-        a.out[i] = linear_tree<N, T, N>(a.vals + base, a.stride, t);
     }
 }
 
@@ -108,43 +277,55 @@ __global__ void __launch_bounds__(kBlock) linear_kernel(const __grid_constant__ 
 // Nearest (ref: nearest/regular.rs:234-295, nearest/rectilinear.rs:193-241)
 // ---------------------------------------------------------------------------------------------
 
-template <class T, int N, bool RECT>
+template <class T, int N, bool RECT, int P>
 __global__ void __launch_bounds__(kBlock) nearest_kernel(const __grid_constant__ EvalArgs<T, N> a) {
-    using O = Ops<T>;
     const T* axes = nullptr;
     if constexpr (RECT) axes = stage_axes<T, N>(a);
-    const T half = T(0.5);
     const unsigned long long gstride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
-    for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n;
-         i += gstride) {
-        long long idx = 0;
-        bool ok = true;
+    const unsigned long long gtid = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const unsigned long long ngroups = a.n / P;
+    for (unsigned long long g = gtid; g < ngroups; g += gstride) {
+        const unsigned long long i0 = g * P;
+        T xs[P][N];
 #pragma unroll
         for (int d = 0; d < N; ++d) {
-            T x = a.obs[d][i];
-            int origin;
-            T dt;
-            if constexpr (RECT) {
-                const T* g = axes + a.axis_off[d];
-                origin = clamp_cell(static_cast<long long>(lower_bound(g, a.dim[d], x)) - 1, a.dim[d] - 2);
-                T x0 = g[origin];
-                T x1 = g[origin + 1];
-                dt = O::div(O::sub(x, x0), O::sub(x1, x0));
-            } else {
-                long long iloc = 0;
-                ok = floor_cell(x, a.start[d], a.step[d], iloc) && ok;
-                origin = clamp_cell(iloc, a.dim[d] - 2);
-                T x0 = O::add(a.start[d], O::mul(a.step[d], O::from_int(origin)));
-                dt = O::div(O::sub(x, x0), a.step[d]);
+            T v[P];
+            load_query_vec<T, P>(a.obs[d] + i0, v);
+#pragma unroll
+            for (int p = 0; p < P; ++p) xs[p][d] = v[p];
+        }
+        long long idx[P];
+        bool ok[P];
+        bool all_ok = true;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            ok[p] = nearest_locate<T, N, RECT>(a, axes, xs[p], idx[p]);
+            all_ok = all_ok && ok[p];
+            if (!ok[p]) idx[p] = 0;
+        }
+        T res[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) res[p] = __ldg(a.vals + idx[p]);
+        if (all_ok) {
+            store_result_vec<T, P>(a.out + i0, res);
+        } else {
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                if (ok[p]) store_result(a.out + i0 + p, res[p]);
+                else report_bad(a.first_bad, a.index_base + i0 + p);
             }
-            int off = (dt <= half) ? 0 : 1;  // tie -> lower index; NaN (rectilinear only) -> upper
-            idx += static_cast<long long>(origin + off) * a.stride[d];
         }
-        if (!ok) {
-            report_bad(a.first_bad, a.index_base + i);
-            continue;
+    }
+    if constexpr (P > 1) {
+        const unsigned long long i = ngroups * P + gtid;
+        if (i < a.n) {
+            T xs[N];
+#pragma unroll
+            for (int d = 0; d < N; ++d) xs[d] = load_query(a.obs[d] + i);
+            long long idx;
+            if (nearest_locate<T, N, RECT>(a, axes, xs, idx)) store_result(a.out + i, __ldg(a.vals + idx));
+            else report_bad(a.first_bad, a.index_base + i);
         }
-        a.out[i] = __ldg(a.vals + idx);
     }
 }
 
@@ -162,52 +343,49 @@ struct CubicRegDim {
     bool lin;  // outside the grid on this dimension AND linearize_extrapolation
 };
 
+// One 1-D cubic step. The five-way saturation switch of the reference is evaluated without
+// divergent branches: both centred slopes are always formed, the operands of the active formula
+// are selected, and the arithmetic that follows is the reference's own sequence for that case, so
+// every lane's result is bit-identical to its branch. `all_none` is warp-uniform (every lane of
+// the warp is in the interior on this dimension) and skips the selects.
 template <class T>
-__device__ __forceinline__ T cubic_regular_step(const T (&v)[4], const CubicRegDim<T>& c) {
+__device__ __forceinline__ T cubic_regular_step(T v0, T v1, T v2, T v3, const CubicRegDim<T>& c, bool all_none) {
     using O = Ops<T>;
     const T half = T(0.5);  // `/ two` is exact and equals `* 0.5` bit-for-bit
     const T two = T(2);
-    if (c.mode == kModeNone) {
-        T dy = O::sub(v[2], v[1]);
-        T k0 = O::mul(O::sub(v[2], v[0]), half);
-        T k1 = O::mul(O::sub(v[3], v[1]), half);
-        return hermite(c.tt, v[1], dy, k0, k1);
-    }
-    T y0, y1, k0;
-    if (c.mode == kModeLow) {
-        y0 = v[1];
-        y1 = v[0];
-        k0 = O::mul(-O::sub(v[2], v[0]), half);
-    } else {
-        y0 = v[2];
-        y1 = v[3];
-        k0 = O::mul(O::sub(v[3], v[1]), half);
-    }
-    T dy = O::sub(y1, y0);
-    T k1 = O::sub(O::mul(two, dy), k0);  // natural-spline end condition
-    if (c.lin) return O::add(y1, O::mul(k1, c.ttm1));
-    return hermite(c.tt, y0, dy, k0, k1);
+    const T sa = O::mul(O::sub(v2, v0), half);  // (v2 - v0) / 2
+    const T sb = O::mul(O::sub(v3, v1), half);  // (v3 - v1) / 2
+    if (all_none) return hermite(c.tt, v1, O::sub(v2, v1), sa, sb);
+    const bool low = c.mode == kModeLow, high = c.mode == kModeHigh;
+    const T y0 = high ? v2 : v1;
+    const T y1 = low ? v0 : (high ? v3 : v2);
+    const T k0 = low ? -sa : (high ? sb : sa);
+    const T dy = O::sub(y1, y0);
+    const T knat = O::sub(O::mul(two, dy), k0);  // natural-spline end condition
+    const T k1 = (low || high) ? knat : sb;
+    const T cub = hermite(c.tt, y0, dy, k0, k1);
+    const T lin = O::add(y1, O::mul(k1, c.ttm1));
+    return c.lin ? lin : cub;
 }
 
 template <class T>
-__device__ __forceinline__ bool cubic_regular_locate(T x, T start, T step, int dim, int linearize, int& origin,
-                                                     CubicRegDim<T>& c) {
+__device__ __forceinline__ bool cubic_regular_locate(T x, T start, T step, T rstep, bool fast, int dim, int linearize,
+                                                     int& origin, CubicRegDim<T>& c) {
     using O = Ops<T>;
-    long long iloc = 0;
-    bool ok = floor_cell(x, start, step, iloc);
-    iloc -= 1;
-    origin = clamp_cell(iloc, dim - 4);
-    const long long n = dim;
+    // f = floor((x - start)/step); the reference's iloc is f - 1 (multicubic/regular.rs:438-440).
+    int f = 0;
+    bool ok = floor_cell(x, start, step, rstep, fast, f);
+    origin = min(max(f, 1) - 1, dim - 4);  // clamp(iloc, 0, dim - 4) without overflow at the saturation ends
     bool outside;
-    if (iloc < -1) { c.mode = kModeLow; outside = true; }
-    else if (iloc == -1) { c.mode = kModeLow; outside = false; }
-    else if (iloc > n - 3) { c.mode = kModeHigh; outside = true; }
-    else if (iloc == n - 3) { c.mode = kModeHigh; outside = false; }
+    if (f < 0) { c.mode = kModeLow; outside = true; }              // iloc < -1
+    else if (f == 0) { c.mode = kModeLow; outside = false; }       // iloc == -1
+    else if (f > dim - 2) { c.mode = kModeHigh; outside = true; }  // iloc > n - 3
+    else if (f == dim - 2) { c.mode = kModeHigh; outside = false; }
     else { c.mode = kModeNone; outside = false; }
     // t is relative to footprint index 1 and its origin coordinate is never fused
     // (ref: multicubic/regular.rs:356-360).
     T x1 = O::add(start, O::mul(step, O::from_int(origin + 1)));
-    T t = O::div(O::sub(x, x1), step);
+    T t = exact_div(O::sub(x, x1), step, rstep, fast);
     const T one = T(1);
     c.tt = c.mode == kModeNone ? t : (c.mode == kModeLow ? -t : O::sub(t, one));
     c.ttm1 = O::sub(c.tt, one);
@@ -225,9 +403,11 @@ struct CubicRectDim {
     T ttm1;
     T wa, wc;  // a and c weights of centered_difference_nonuniform for k0 (ref: multicubic/mod.rs:104,106)
     T div0;    // the non-unit spacing ratio k0's data-dependent quotient divides by
-    T wa1, wc1, div1;  // same for k1 (interior cells only)
+    T rdiv0;   // RN(1 / div0), for exact_div
+    T wa1, wc1, div1, rdiv1;  // same for k1 (interior cells only)
     int mode;
     bool lin;
+    bool fast;  // div0 and div1 are in exact_div's exponent range
 };
 
 template <class T>
@@ -235,8 +415,8 @@ __device__ __forceinline__ void cubic_rect_locate(T x, const T* __restrict__ g, 
                                                   CubicRectDim<T>& c) {
     using O = Ops<T>;
     const T one = T(1);
-    const long long n = dim;
-    long long iloc = static_cast<long long>(lower_bound(g, dim, x)) - 2;
+    const int n = dim;
+    const int iloc = lower_bound(g, dim, x) - 2;
     origin = clamp_cell(iloc, dim - 4);
     bool outside;
     if (iloc == -2) { c.mode = kModeLow; outside = true; }
@@ -273,40 +453,43 @@ __device__ __forceinline__ void cubic_rect_locate(T x, const T* __restrict__ g, 
         c.div0 = p;
         c.tt = O::div(O::sub(x, g2), h23);
     }
+    c.rdiv0 = O::div(one, c.div0);
+    c.rdiv1 = O::div(one, c.div1);
+    c.fast = exact_div_divisor_ok(c.div0) && exact_div_divisor_ok(c.div1);
     c.ttm1 = O::sub(c.tt, one);
     c.lin = outside && linearize;
 }
 
 // centered_difference_nonuniform(y0,y1,y2,h01,h12) = a*b + c*d with the unit-spacing divisions
-// (x / 1.0, exact) dropped (ref: multicubic/mod.rs:103-117, rectilinear.rs:449-450).
+// (x / 1.0, exact) dropped (ref: multicubic/mod.rs:103-117, rectilinear.rs:449-450). Like the
+// regular-grid step this is select-based: the one data-dependent quotient of k0 picks its
+// numerator by case; k1's quotient exists only in the interior case.
 template <class T>
-__device__ __forceinline__ T cubic_rect_step(const T (&v)[4], const CubicRectDim<T>& c) {
+__device__ __forceinline__ T cubic_rect_step(T v0, T v1, T v2, T v3, const CubicRectDim<T>& c, bool all_none) {
     using O = Ops<T>;
     const T two = T(2);
-    if (c.mode == kModeNone) {
-        T dy = O::sub(v[2], v[1]);
-        // k0: h01 = r, h12 = 1 -> b = (v2-v1)/1, d = (v1-v0)/r
-        T k0 = O::add(O::mul(c.wa, dy), O::mul(c.wc, O::div(O::sub(v[1], v[0]), c.div0)));
-        // k1: h01 = 1, h12 = s -> b = (v3-v2)/s, d = (v2-v1)/1
-        T k1 = O::add(O::mul(c.wa1, O::div(O::sub(v[3], v[2]), c.div1)), O::mul(c.wc1, dy));
-        return hermite(c.tt, v[1], dy, k0, k1);
+    const T d10 = O::sub(v1, v0), d21 = O::sub(v2, v1), d32 = O::sub(v3, v2);
+    if (all_none) {
+        // k0: h01 = r, h12 = 1 -> b = (v2-v1)/1, d = (v1-v0)/r;  k1: h01 = 1, h12 = s -> b = (v3-v2)/s, d = (v2-v1)/1
+        T k0 = O::add(O::mul(c.wa, d21), O::mul(c.wc, exact_div(d10, c.div0, c.rdiv0, c.fast)));
+        T k1 = O::add(O::mul(c.wa1, exact_div(d32, c.div1, c.rdiv1, c.fast)), O::mul(c.wc1, d21));
+        return hermite(c.tt, v1, d21, k0, k1);
     }
-    T y0, y1, k0;
-    if (c.mode == kModeLow) {
-        y0 = v[1];
-        y1 = v[0];
-        // cdn(v0,v1,v2, 1, q): b = (v2-v1)/q, d = (v1-v0)/1
-        k0 = -O::add(O::mul(c.wa, O::div(O::sub(v[2], v[1]), c.div0)), O::mul(c.wc, O::sub(v[1], v[0])));
-    } else {
-        y0 = v[2];
-        y1 = v[3];
-        // cdn(v1,v2,v3, p, 1): b = (v3-v2)/1, d = (v2-v1)/p
-        k0 = O::add(O::mul(c.wa, O::sub(v[3], v[2])), O::mul(c.wc, O::div(O::sub(v[2], v[1]), c.div0)));
-    }
-    T dy = O::sub(y1, y0);
+    const bool low = c.mode == kModeLow, high = c.mode == kModeHigh, none = !(low || high);
+    const T q0 = exact_div(none ? d10 : d21, c.div0, c.rdiv0, c.fast);
+    // None: wa*(v2-v1) + wc*((v1-v0)/r)   Low: -(wa*((v2-v1)/q) + wc*(v1-v0))   High: wa*(v3-v2) + wc*((v2-v1)/p)
+    const T pa = none ? d21 : (low ? q0 : d32);
+    const T pc = low ? d10 : q0;
+    const T k0r = O::add(O::mul(c.wa, pa), O::mul(c.wc, pc));
+    const T k0 = low ? -k0r : k0r;
+    const T y0 = high ? v2 : v1;
+    const T y1 = low ? v0 : (high ? v3 : v2);
+    const T dy = none ? d21 : (low ? -d10 : d32);  // v0 - v1 == -(v1 - v0) exactly
     T k1 = O::sub(O::mul(two, dy), k0);
-    if (c.lin) return O::add(y1, O::mul(k1, c.ttm1));
-    return hermite(c.tt, y0, dy, k0, k1);
+    if (none) k1 = O::add(O::mul(c.wa1, exact_div(d32, c.div1, c.rdiv1, c.fast)), O::mul(c.wc1, d21));
+    const T cub = hermite(c.tt, y0, dy, k0, k1);
+    const T lin = O::add(y1, O::mul(k1, c.ttm1));
+    return c.lin ? lin : cub;
 }
 
 template <class T, bool RECT>
@@ -319,22 +502,31 @@ struct CubicDimOf<T, true> {
 };
 
 template <class T, bool RECT>
-__device__ __forceinline__ T cubic_step(const T (&v)[4], const typename CubicDimOf<T, RECT>::type& c) {
-    if constexpr (RECT) return cubic_rect_step(v, c);
-    else return cubic_regular_step(v, c);
+__device__ __forceinline__ T cubic_step(T v0, T v1, T v2, T v3, const typename CubicDimOf<T, RECT>::type& c,
+                                        bool all_none) {
+    if constexpr (RECT) return cubic_rect_step(v0, v1, v2, v3, c, all_none);
+    else return cubic_regular_step(v0, v1, v2, v3, c, all_none);
 }
 
-// Fully unrolled 4^N tree (N <= 4, the reference's "flattened" range).
-template <int D, class T, int N, bool RECT>
-__device__ __forceinline__ T cubic_tree(const T* __restrict__ p, const long long (&stride)[N],
-                                        const typename CubicDimOf<T, RECT>::type (&c)[N]) {
+// Fully unrolled 4^N footprint (N <= 4, the reference's "flattened" range), row by row: reduces
+// dimensions 0..D-1 of the sub-block at `idx` for all four positions of the last (contiguous)
+// dimension at once, dimension 0 innermost like the reference (multicubic/regular.rs:383-412).
+template <int D, class T, int N, bool RECT, bool WIN>
+__device__ __forceinline__ void cubic_rows(const T* __restrict__ vals, const T* __restrict__ win, long long idx,
+                                           const long long (&stride)[N],
+                                           const typename CubicDimOf<T, RECT>::type (&c)[N], unsigned none_mask,
+                                           T (&out)[4]) {
     if constexpr (D == 0) {
-        return __ldg(p);
+        load_row<T, 4, WIN>(vals, win, idx, out);
     } else {
-        T v[4];
+        T sub[4][4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = cubic_tree<D - 1, T, N, RECT>(p + k * stride[D - 1], stride, c);
-        return cubic_step<T, RECT>(v, c[D - 1]);
+        for (int k = 0; k < 4; ++k)
+            cubic_rows<D - 1, T, N, RECT, WIN>(vals, win, idx + k * stride[D - 1], stride, c, none_mask, sub[k]);
+        const bool all_none = (none_mask >> (D - 1)) & 1u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            out[j] = cubic_step<T, RECT>(sub[0][j], sub[1][j], sub[2][j], sub[3][j], c[D - 1], all_none);
     }
 }
 
@@ -355,40 +547,60 @@ __device__ __noinline__ T cubic_tree_loop(const T* __restrict__ p, const long lo
             const unsigned q = 1u << (2 * j);
             if (((i + 1) & (q - 1)) == 0) {
                 const unsigned slot = (((i + 1) >> (2 * j)) - 1) & 3u;
-                store[j][slot] = cubic_step<T, RECT>(store[j - 1], c[j - 1]);
+                const T(&s)[4] = store[j - 1];
+                store[j][slot] = cubic_step<T, RECT>(s[0], s[1], s[2], s[3], c[j - 1], false);
             }
         }
     }
-    return cubic_step<T, RECT>(store[N - 1], c[N - 1]);
+    const T(&s)[4] = store[N - 1];
+    return cubic_step<T, RECT>(s[0], s[1], s[2], s[3], c[N - 1], false);
 }
 
-template <class T, int N, bool RECT>
-__global__ void __launch_bounds__(kBlock) cubic_kernel(const __grid_constant__ EvalArgs<T, N> a) {
+// MINB = CTAs per SM the register allocation must allow (launch_common.cuh cubic_min_blocks).
+template <class T, int N, bool RECT, bool WIN, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) cubic_kernel(const __grid_constant__ EvalArgs<T, N> a) {
     const T* axes = nullptr;
     if constexpr (RECT) axes = stage_axes<T, N>(a);
     const unsigned long long gstride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
-    for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n;
-         i += gstride) {
+    // Whole warps iterate together (lanes past the end are masked) so the per-dimension
+    // "every lane is interior" votes are warp-uniform.
+    for (unsigned long long i0 = static_cast<unsigned long long>(blockIdx.x) * blockDim.x; i0 < a.n; i0 += gstride) {
+        const unsigned long long i = i0 + threadIdx.x;
+        const bool valid = i < a.n;
+        const unsigned long long il = valid ? i : a.n - 1;
+        T xs[N];
+#pragma unroll
+        for (int d = 0; d < N; ++d) xs[d] = load_query(a.obs[d] + il);
         typename CubicDimOf<T, RECT>::type c[N];
         long long base = 0;
         bool ok = true;
+        unsigned none_mask = 0;
 #pragma unroll
         for (int d = 0; d < N; ++d) {
-            T x = a.obs[d][i];
+            const T x = xs[d];
             int origin;
             if constexpr (RECT) {
                 cubic_rect_locate(x, axes + a.axis_off[d], a.dim[d], a.linearize, origin, c[d]);
             } else {
-                ok = cubic_regular_locate(x, a.start[d], a.step[d], a.dim[d], a.linearize, origin, c[d]) && ok;
+                ok = cubic_regular_locate(x, a.start[d], a.step[d], a.rstep[d], a.fast_div != 0, a.dim[d], a.linearize, origin,
+                                          c[d]) && ok;
             }
             base += static_cast<long long>(origin) * a.stride[d];
+            if constexpr (N <= 4) none_mask |= __all_sync(0xffffffffu, c[d].mode == kModeNone) ? (1u << d) : 0u;
         }
         if (!ok) {
-            report_bad(a.first_bad, a.index_base + i);
+            if (valid) report_bad(a.first_bad, a.index_base + i);
             continue;
         }
-        if constexpr (N <= 4) a.out[i] = cubic_tree<N, T, N, RECT>(a.vals + base, a.stride, c);
-        else a.out[i] = cubic_tree_loop<T, N, RECT>(a.vals + base, a.stride, c);
+        T res;
+        if constexpr (N <= 4) {
+            T r[4];
+            cubic_rows<N - 1, T, N, RECT, WIN>(a.vals, a.win, base, a.stride, c, none_mask, r);
+            res = cubic_step<T, RECT>(r[0], r[1], r[2], r[3], c[N - 1], (none_mask >> (N - 1)) & 1u);
+        } else {
+            res = cubic_tree_loop<T, N, RECT>(a.vals + base, a.stride, c);
+        }
+        if (valid) store_result(a.out + i, res);
     }
 }
 

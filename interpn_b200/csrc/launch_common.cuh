@@ -19,11 +19,20 @@ inline EvalArgs<T, N> make_args(const DeviceGrid& g, const T* const* obs, size_t
         a.dim[d] = g.dim[d];
         a.start[d] = static_cast<T>(g.start[d]);
         a.step[d] = static_cast<T>(g.step[d]);
+        a.rstep[d] = T(1) / a.step[d];  // correctly rounded in T (host IEEE division)
         a.axis_off[d] = g.axis_off[d];
     }
     a.out = out;
     a.n = n;
     a.vals = static_cast<const T*>(g.vals);
+    a.win = static_cast<const T*>(g.win);
+    a.fast_div = 0;
+    if (!g.rect && sizeof(T) == 8) {
+        // exact_div's divisor guard (device_math.cuh): 2^-300 <= step < 2^301 on every dimension
+        a.fast_div = 1;
+        for (int d = 0; d < N; ++d)
+            if (!(g.step[d] >= 0x1p-300 && g.step[d] < 0x1p301)) a.fast_div = 0;
+    }
     a.axes = static_cast<const T*>(g.axes);
     a.axes_total = g.axes_total;
     a.axes_in_smem = g.rect && static_cast<size_t>(g.axes_total) * sizeof(T) <= kAxesSmemBudget;
@@ -40,10 +49,34 @@ inline unsigned grid_for(size_t n, int sm_count, int ctas_per_sm) {
     return static_cast<unsigned>(want < cap ? (want ? want : 1) : cap);
 }
 
+// True when every coordinate array and `out` can be accessed as vectors of P elements.
+template <class T>
+inline bool vector_aligned(const T* const* obs, int ndims, const T* out, int P) {
+    const uintptr_t mask = static_cast<uintptr_t>(P) * sizeof(T) - 1;
+    uintptr_t bits = reinterpret_cast<uintptr_t>(out);
+    for (int d = 0; d < ndims; ++d) bits |= reinterpret_cast<uintptr_t>(obs[d]);
+    return (bits & mask) == 0;
+}
+
+// Points per thread of the streaming kernels (kernels.cuh linear_kernel / nearest_kernel).
+#ifndef IB200_P_NEAREST
+#define IB200_P_NEAREST 4
+#endif
+#ifndef IB200_P_LINEAR_LO
+#define IB200_P_LINEAR_LO 4  // N <= 3
+#endif
+#ifndef IB200_P_LINEAR_HI
+#define IB200_P_LINEAR_HI 2  // N = 4, 5
+#endif
+template <int N>
+constexpr int linear_points_per_thread() {
+    return N <= 3 ? IB200_P_LINEAR_LO : (N <= 5 ? IB200_P_LINEAR_HI : 1);
+}
+
 template <class T, int N, class K>
 inline cudaError_t launch_generic(K kernel, const DeviceGrid& g, const T* const* obs, size_t n, T* out,
                                   unsigned long long* first_bad, unsigned long long index_base, cudaStream_t stream,
-                                  int ctas_per_sm = 8) {
+                                  int points_per_thread = 1, int ctas_per_sm = 8) {
     if (n == 0) return cudaSuccess;
     EvalArgs<T, N> a = make_args<T, N>(g, obs, n, out, first_bad, index_base);
     size_t smem = a.axes_in_smem ? static_cast<size_t>(g.axes_total) * sizeof(T) : 0;
@@ -51,9 +84,37 @@ inline cudaError_t launch_generic(K kernel, const DeviceGrid& g, const T* const*
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
     }
-    kernel<<<grid_for(n, g.sm_count, ctas_per_sm), kBlock, smem, stream>>>(a);
+    const size_t work = (n + points_per_thread - 1) / points_per_thread;
+    kernel<<<grid_for(work, g.sm_count, ctas_per_sm), kBlock, smem, stream>>>(a);
     count_launch();
     return cudaGetLastError();
+}
+
+// Window-layout kernels are instantiated up to these dimensionalities (interp_internal.h mirrors them
+// in window_policy): the cubic footprint is unrolled row by row only in the flattened range N <= 4.
+constexpr int kMaxWindowDimsLinear = 6;
+constexpr int kMaxWindowDimsCubic = 4;
+
+// Register budget of the unrolled cubic kernels, as resident CTAs (of kBlock threads) per SM. The
+// footprint of a 3-D / 4-D cubic is 64 / 256 gathers deep, so these kernels live on latency hiding:
+// the values below are the measured optimum between spilling and occupancy.
+#ifndef IB200_MINB_CUBIC3
+#define IB200_MINB_CUBIC3 2
+#endif
+#ifndef IB200_MINB_CUBIC4
+#define IB200_MINB_CUBIC4 3
+#endif
+#ifndef IB200_MINB_CUBIC3_RECT
+#define IB200_MINB_CUBIC3_RECT 2
+#endif
+#ifndef IB200_MINB_CUBIC4_RECT
+#define IB200_MINB_CUBIC4_RECT 3
+#endif
+template <int N, bool RECT>
+constexpr int cubic_min_blocks() {
+    if (N == 3) return RECT ? IB200_MINB_CUBIC3_RECT : IB200_MINB_CUBIC3;
+    if (N == 4) return RECT ? IB200_MINB_CUBIC4_RECT : IB200_MINB_CUBIC4;
+    return 1;
 }
 
 #define IB200_SWITCH_N(NMAX, BODY)                     \
@@ -62,8 +123,8 @@ inline cudaError_t launch_generic(K kernel, const DeviceGrid& g, const T* const*
         case 2: { constexpr int N = 2; BODY } break;   \
         case 3: { constexpr int N = 3; BODY } break;   \
         case 4: { constexpr int N = 4; BODY } break;   \
-        case 5: { constexpr int N = 5; BODY } break;   \
-        case 6: { constexpr int N = 6; BODY } break;   \
+        case 5: if constexpr (NMAX >= 5) { constexpr int N = 5; BODY } break; \
+        case 6: if constexpr (NMAX >= 6) { constexpr int N = 6; BODY } break; \
         case 7: if constexpr (NMAX >= 7) { constexpr int N = 7; BODY } break; \
         case 8: if constexpr (NMAX >= 8) { constexpr int N = 8; BODY } break; \
         default: break;                                \

@@ -3,14 +3,32 @@
 
 namespace ib200 {
 
+template <class T, int N, bool RECT, bool WIN>
+cudaError_t launch_linear_n(const DeviceGrid& g, const T* const* obs, size_t n, T* out, unsigned long long* first_bad,
+                            unsigned long long index_base, cudaStream_t stream) {
+    constexpr int P = linear_points_per_thread<N>();
+    if (P > 1 && n >= static_cast<size_t>(P) && vector_aligned<T>(obs, N, out, P))
+        return launch_generic<T, N>(linear_kernel<T, N, RECT, WIN, P>, g, obs, n, out, first_bad, index_base, stream, P);
+    return launch_generic<T, N>(linear_kernel<T, N, RECT, WIN, 1>, g, obs, n, out, first_bad, index_base, stream);
+}
+
 template <class T>
 cudaError_t launch_linear(const DeviceGrid& g, const T* const* obs, size_t n, T* out, unsigned long long* first_bad,
                           unsigned long long index_base, cudaStream_t stream) {
     cudaError_t err = cudaErrorInvalidValue;
+    const bool win = g.win != nullptr && g.win_width == 2 && g.ndims <= kMaxWindowDimsLinear;
     if (g.rect) {
-        IB200_SWITCH_N(8, err = (launch_generic<T, N>(linear_kernel<T, N, true>, g, obs, n, out, first_bad, index_base, stream));)
+        if (win) {
+            IB200_SWITCH_N(kMaxWindowDimsLinear, err = (launch_linear_n<T, N, true, true>(g, obs, n, out, first_bad, index_base, stream));)
+        } else {
+            IB200_SWITCH_N(8, err = (launch_linear_n<T, N, true, false>(g, obs, n, out, first_bad, index_base, stream));)
+        }
     } else {
-        IB200_SWITCH_N(8, err = (launch_generic<T, N>(linear_kernel<T, N, false>, g, obs, n, out, first_bad, index_base, stream));)
+        if (win) {
+            IB200_SWITCH_N(kMaxWindowDimsLinear, err = (launch_linear_n<T, N, false, true>(g, obs, n, out, first_bad, index_base, stream));)
+        } else {
+            IB200_SWITCH_N(8, err = (launch_linear_n<T, N, false, false>(g, obs, n, out, first_bad, index_base, stream));)
+        }
     }
     return err;
 }

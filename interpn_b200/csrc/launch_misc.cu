@@ -4,6 +4,36 @@
 namespace ib200 {
 
 // ---------------------------------------------------------------------------------------------
+// Window layout builder: win[f*W + j] = vals[min(f + j, nvals - 1)]  (kernels.cuh load_row)
+// ---------------------------------------------------------------------------------------------
+
+template <class T, int W>
+__global__ void __launch_bounds__(kBlock) build_window_kernel(const T* __restrict__ vals, T* __restrict__ win,
+                                                              unsigned long long nvals) {
+    const unsigned long long total = nvals * W;
+    const unsigned long long gstride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+    for (unsigned long long k = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; k < total;
+         k += gstride) {
+        unsigned long long src = k / W + k % W;
+        win[k] = vals[src < nvals ? src : nvals - 1];
+    }
+}
+
+cudaError_t launch_build_window(const DeviceGrid& g, cudaStream_t stream) {
+    if (!g.win || g.nvals == 0) return cudaSuccess;
+    const unsigned grid_dim = grid_for(g.nvals * g.win_width, g.sm_count, 8);
+    if (g.elem == 8) {
+        if (g.win_width == 4) build_window_kernel<double, 4><<<grid_dim, kBlock, 0, stream>>>(static_cast<const double*>(g.vals), static_cast<double*>(g.win), g.nvals);
+        else build_window_kernel<double, 2><<<grid_dim, kBlock, 0, stream>>>(static_cast<const double*>(g.vals), static_cast<double*>(g.win), g.nvals);
+    } else {
+        if (g.win_width == 4) build_window_kernel<float, 4><<<grid_dim, kBlock, 0, stream>>>(static_cast<const float*>(g.vals), static_cast<float*>(g.win), g.nvals);
+        else build_window_kernel<float, 2><<<grid_dim, kBlock, 0, stream>>>(static_cast<const float*>(g.vals), static_cast<float*>(g.win), g.nvals);
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 // one_dim (ref: one_dim/mod.rs:85-187, one_dim/linear.rs:24-85, one_dim/hold.rs:23-107)
 // ---------------------------------------------------------------------------------------------
 
@@ -33,7 +63,7 @@ __global__ void __launch_bounds__(kBlock) one_dim_kernel(const __grid_constant__
         int cell, extrap = kInside;
         T x0, x1;
         if constexpr (RECT) {
-            cell = clamp_cell(static_cast<long long>(lower_bound(a.grid, a.nvals, loc)) - 1, a.nvals - 2);
+            cell = clamp_cell(lower_bound(a.grid, a.nvals, loc) - 1, a.nvals - 2);
             if (loc < a.grid[0]) extrap = kOutsideLow;
             else if (loc > a.grid[a.nvals - 1]) extrap = kOutsideHigh;
             x0 = a.grid[cell];
@@ -41,8 +71,8 @@ __global__ void __launch_bounds__(kBlock) one_dim_kernel(const __grid_constant__
         } else {
             if (loc > a.stop) extrap = kOutsideHigh;
             else if (loc < a.start) extrap = kOutsideLow;
-            long long iloc = 0;
-            if (!floor_cell(loc, a.start, a.step, iloc)) {
+            int iloc = 0;
+            if (!floor_cell(loc, a.start, a.step, a.step, false, iloc)) {
                 report_bad(a.first_bad, a.index_base + i);
                 continue;
             }

@@ -7,10 +7,20 @@ template <class T>
 cudaError_t launch_nearest(const DeviceGrid& g, const T* const* obs, size_t n, T* out, unsigned long long* first_bad,
                            unsigned long long index_base, cudaStream_t stream) {
     cudaError_t err = cudaErrorInvalidValue;
+    constexpr int P = IB200_P_NEAREST;
+    const bool vec = P > 1 && n >= static_cast<size_t>(P) && vector_aligned<T>(obs, g.ndims, out, P);
     if (g.rect) {
-        IB200_SWITCH_N(6, err = (launch_generic<T, N>(nearest_kernel<T, N, true>, g, obs, n, out, first_bad, index_base, stream));)
+        if (vec) {
+            IB200_SWITCH_N(6, err = (launch_generic<T, N>(nearest_kernel<T, N, true, P>, g, obs, n, out, first_bad, index_base, stream, P));)
+        } else {
+            IB200_SWITCH_N(6, err = (launch_generic<T, N>(nearest_kernel<T, N, true, 1>, g, obs, n, out, first_bad, index_base, stream));)
+        }
     } else {
-        IB200_SWITCH_N(6, err = (launch_generic<T, N>(nearest_kernel<T, N, false>, g, obs, n, out, first_bad, index_base, stream));)
+        if (vec) {
+            IB200_SWITCH_N(6, err = (launch_generic<T, N>(nearest_kernel<T, N, false, P>, g, obs, n, out, first_bad, index_base, stream, P));)
+        } else {
+            IB200_SWITCH_N(6, err = (launch_generic<T, N>(nearest_kernel<T, N, false, 1>, g, obs, n, out, first_bad, index_base, stream));)
+        }
     }
     return err;
 }

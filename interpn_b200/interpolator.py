@@ -186,6 +186,11 @@ class Interpolator:
         t._interpn_owner = self  # keep the storage alive while the alias exists
         return t
 
+    def vals_updated(self, stream: int = 0) -> None:
+        """Tell the library the resident `vals` were rewritten through `vals_ptr` / `vals_tensor()`
+        (e.g. by the grid broadcast): refreshes its gather-optimised copies, ordered on `stream`."""
+        _lib.check(lib.interpn_b200_interp_vals_updated(self._h, C.c_void_p(int(stream))))
+
     def close(self) -> None:
         if self._h:
             lib.interpn_b200_interp_free(self._h)

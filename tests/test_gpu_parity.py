@@ -262,6 +262,7 @@ def test_vals_from_device_and_uninitialised_storage(ib):
     assert c.vals_len == vals.size and c.vals_ptr != 0
     # fill c's storage the way the multi-GPU broadcast does: through a tensor aliasing the resident copy
     c.vals_tensor().copy_(torch.from_numpy(vals).cuda())
+    c.vals_updated(torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     ra, rb, rc = a.eval(obs), b.eval(obs), c.eval(obs)
     assert_same_bits(ra, rb)

@@ -69,6 +69,98 @@ __global__ void smem_gather_kernel(const double* __restrict__ tab, int n, int pe
     if (s == 123.456) out[0] = s;
 }
 
+
+// ---- second-generation probes: cheap index generation (LCG + mulhi) so the load path, not the
+// integer pipe, is what saturates.
+__device__ __forceinline__ unsigned lcg(unsigned& x) { x = x * 1664525u + 1013904223u; return x; }
+
+struct __align__(32) D4 { double x, y, z, w; };
+struct __align__(16) D2 { double x, y; };
+
+// MODE 0: one 32-byte aligned LDG.256 per row (window layout); 1: 4 x LDG.64 at an arbitrary 8-byte
+// offset; 2: 2 x LDG.128 at a 16-byte aligned offset; 3: one LDG.128 (pair layout); 4: one LDG.64.
+template <int MODE>
+__global__ void row_gather_kernel(const double* __restrict__ tab, unsigned nrows_or_n, int per, double* out) {
+    unsigned x = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    double s = 0;
+    for (int i = 0; i < per; i += 8) {
+        double v[8][4];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            unsigned r = __umulhi(lcg(x), nrows_or_n);
+            if (MODE == 0) {
+                D4 q = reinterpret_cast<const D4*>(tab)[r];
+                v[k][0] = q.x; v[k][1] = q.y; v[k][2] = q.z; v[k][3] = q.w;
+            } else if (MODE == 1) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[k][j] = __ldg(tab + r + j);
+            } else if (MODE == 2) {
+                D2 a = reinterpret_cast<const D2*>(tab)[r], b = reinterpret_cast<const D2*>(tab)[r + 1];
+                v[k][0] = a.x; v[k][1] = a.y; v[k][2] = b.x; v[k][3] = b.y;
+            } else if (MODE == 3) {
+                D2 a = reinterpret_cast<const D2*>(tab)[r];
+                v[k][0] = a.x; v[k][1] = a.y; v[k][2] = 0; v[k][3] = 0;
+            } else {
+                v[k][0] = __ldg(tab + r); v[k][1] = v[k][2] = v[k][3] = 0;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += (v[k][0] + v[k][1]) + (v[k][2] + v[k][3]);
+    }
+    if (s == 123.456) out[0] = s;
+}
+
+// Random shared-memory gathers with cheap indices. W = 1: LDS.64, 2: LDS.128 (16-byte aligned pair).
+template <int W>
+__global__ void smem_gather2_kernel(const double* __restrict__ tab, int n, int per, double* out) {
+    extern __shared__ __align__(16) double sm[];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sm[i] = tab[i];
+    __syncthreads();
+    unsigned x = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 777u;
+    double s0 = 0, s1 = 0;
+    for (int i = 0; i < per; i += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (W == 1) {
+                unsigned idx = __umulhi(lcg(x), (unsigned)n);
+                s0 += sm[idx];
+            } else {
+                unsigned idx = __umulhi(lcg(x), (unsigned)(n / 2));
+                D2 q = reinterpret_cast<const D2*>(sm)[idx];
+                s0 += q.x; s1 += q.y;
+            }
+        }
+    }
+    if (s0 + s1 == 123.456) out[0] = s0;
+}
+
+// Division probes. MODE 0: __ddiv_rn(a, b); 1: reciprocal-residual sequence (5 FP64 ops, b fixed).
+template <int MODE>
+__global__ void div_kernel(double* out, int iters, double b, double rb) {
+    double a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = 1.0 + k + threadIdx.x * 1e-3;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            double q;
+            if (MODE == 0) q = __ddiv_rn(a[k], b);
+            else {
+                double q0 = __dmul_rn(a[k], rb);
+                double e0 = __fma_rn(-q0, b, a[k]);
+                double q1 = __fma_rn(e0, rb, q0);
+                double e1 = __fma_rn(-q1, b, a[k]);
+                q = __fma_rn(e1, rb, q1);
+            }
+            a[k] = __dadd_rn(q, 1.0);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += a[k];
+    if (s == 123.456) out[0] = s;
+}
+
 template <class F>
 float time_ms(F f, int reps = 5) {
     cudaEvent_t a, b;
@@ -124,6 +216,46 @@ int main() {
         float t = time_ms([&] { smem_gather_kernel<<<blocks, threads, n * sizeof(double)>>>(tab, n, per, out); });
         printf(", \"smem_gather8B_random_Gloads_s\": %.2f", loads / t * 1e-6);
         CK(cudaFree(tab));
+    }
+
+    // ---- row gathers from L2-resident tables, cheap indices
+    {
+        const int per = 256, blocks = sms * 16, threads = 256;
+        double rows = double(blocks) * threads * per;
+        const unsigned n32 = 4000000;  // 32 MB window layout of a 100^3 grid (4 doubles per row)
+        double* tab; CK(cudaMalloc(&tab, size_t(n32) * 8 + 64)); CK(cudaMemset(tab, 0, size_t(n32) * 8 + 64));
+        float t0 = time_ms([&] { row_gather_kernel<0><<<blocks, threads>>>(tab, n32 / 4, per, out); });
+        float t1 = time_ms([&] { row_gather_kernel<1><<<blocks, threads>>>(tab, 1000000 - 4, per, out); });
+        float t2 = time_ms([&] { row_gather_kernel<2><<<blocks, threads>>>(tab, 500000 - 2, per, out); });
+        float t3 = time_ms([&] { row_gather_kernel<3><<<blocks, threads>>>(tab, 1000000, per, out); });
+        float t4 = time_ms([&] { row_gather_kernel<4><<<blocks, threads>>>(tab, 1000000, per, out); });
+        float t5 = time_ms([&] { row_gather_kernel<4><<<blocks, threads>>>(tab, 4096, per, out); });
+        float t6 = time_ms([&] { row_gather_kernel<0><<<blocks, threads>>>(tab, 1024, per, out); });
+        printf(", \"row32B_ldg256_L2_Grows_s\": %.2f, \"row4x_ldg64_L2_Grows_s\": %.2f, \"row2x_ldg128_L2_Grows_s\": %.2f"
+               ", \"pair_ldg128_L2_Gloads_s\": %.2f, \"ldg64_L2_Gloads_s\": %.2f, \"ldg64_L1hit_Gloads_s\": %.2f, \"ldg256_L1hit_Grows_s\": %.2f",
+               rows / t0 * 1e-6, rows / t1 * 1e-6, rows / t2 * 1e-6, rows / t3 * 1e-6, rows / t4 * 1e-6, rows / t5 * 1e-6, rows / t6 * 1e-6);
+        CK(cudaFree(tab));
+    }
+    // ---- shared-memory gathers, cheap indices (96 KB tile, 2 CTAs per SM)
+    {
+        const int n = 12288, per = 4096, blocks = sms * 2, threads = 512;
+        double* tab; CK(cudaMalloc(&tab, n * sizeof(double))); CK(cudaMemset(tab, 0, n * sizeof(double)));
+        CK(cudaFuncSetAttribute(smem_gather2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, n * 8));
+        CK(cudaFuncSetAttribute(smem_gather2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, n * 8));
+        double loads = double(blocks) * threads * per;
+        float t1 = time_ms([&] { smem_gather2_kernel<1><<<blocks, threads, n * sizeof(double)>>>(tab, n, per, out); });
+        float t2 = time_ms([&] { smem_gather2_kernel<2><<<blocks, threads, n * sizeof(double)>>>(tab, n, per, out); });
+        printf(", \"lds64_random_Gloads_s\": %.2f, \"lds128_random_Gloads_s\": %.2f", loads / t1 * 1e-6, loads / t2 * 1e-6);
+        CK(cudaFree(tab));
+    }
+    // ---- FP64 division
+    {
+        const int iters = 1024, blocks = sms * 8, threads = 256;
+        double ops = double(blocks) * threads * iters * 8;
+        const double b = 100.0 / 99.0;
+        float t0 = time_ms([&] { div_kernel<0><<<blocks, threads>>>(out, iters, b, 1.0 / b); });
+        float t1 = time_ms([&] { div_kernel<1><<<blocks, threads>>>(out, iters, b, 1.0 / b); });
+        printf(", \"ddiv_rn_Gdiv_s\": %.2f, \"recip_residual_div_Gdiv_s\": %.2f", ops / t0 * 1e-6, ops / t1 * 1e-6);
     }
     printf("}\n");
     return 0;

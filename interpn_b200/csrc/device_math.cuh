@@ -81,7 +81,7 @@ __device__ __forceinline__ int lower_bound(const T* __restrict__ g, int n, T v) 
 // general division sequence (measured 2.4x the throughput, profiles/r1_microbench_b200.json). The
 // theorem needs every intermediate to stay normal, hence the exponent guards: operands outside the
 // guarded range (zeros, subnormals, infinities, NaN, huge or tiny magnitudes) take the true
-// division. tests/test_exact_div.py re-checks the sequence against `/` on adversarial operand
+// division. tests/test_numeric_tricks.py re-checks the sequence against `/` on adversarial operand
 // pairs on the CPU, and the GPU parity suite compares whole evaluations bit for bit.
 // f32 keeps the true division (cheap on the FP32 pipe).
 // ---------------------------------------------------------------------------------------------
@@ -117,6 +117,65 @@ __device__ __forceinline__ bool floor_cell(T v, T start, T step, T rstep, bool f
     const T q = exact_div(O::sub(v, start), step, rstep, fast);
     iloc = O::floor_sat(q);
     return q >= T(-9223372036854775808.0) && q < T(9223372036854775808.0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Division-free cell location for regular f64 grids (the streaming kernels are instruction-issue
+// bound). All three pieces return the reference's bits or report "not sure", in which
+// case the caller re-evaluates the point with the true divisions above. Preconditions checked on the
+// host (launch_common.cuh make_args -> fast_div): 2^-300 <= step < 2^301 and dim < 2^30.
+//
+//  * fast_cell: the approximate quotient q~ = RN(d * RN(1/step)) is within 2^-52 |Q| of Q = d/step, so
+//    f~ = floor(q~) can differ from the reference's floor(RN(Q)) only when Q is that close to an
+//    integer. For an unclamped f~ the FMA remainder r = RN(d - f~*step) (sign-exact, one rounding)
+//    proves the cell: 0 <= r <= step*(1 - 2^-20) implies f~ <= Q <= f~ + 1 - 2^-20, and since
+//    |RN(Q) - Q| <= 2^-53 * 2^31, floor(RN(Q)) = f~. A clamped f~ (f~ < 0 or f~ > dim-2, |f~| <= 2^30)
+//    needs no proof: the true floor is within 1 of f~, hence on the same side of the clamp, and
+//    linear / nearest evaluation uses the clamped origin only. NaN and +-inf never pass
+//    (r is NaN, or f~ saturates beyond 2^30), so the caller's exact path reports them.
+//  * nearest_upper: the reference picks the upper node iff !(RN(e/step) <= 0.5). RN is monotone and
+//    0.5 has an even significand, so RN(y) <= 0.5 <=> y <= 0.5 + 2^-54, i.e. e - step/2 <= step*2^-54.
+//    e - step/2 is exact whenever e is within a factor 2 of step/2 (Sterbenz) and far from the
+//    threshold otherwise, so the FP comparison decides exactly like the division.
+//  * markstein_div: exact_div's sequence without the branch; valid (== RN(a/b)) when
+//    markstein_operand_ok(a) (normal range, or zero — the copysign keeps -0/b = -0).
+// tests/test_numeric_tricks.py re-checks all three against IEEE division on the CPU.
+// ---------------------------------------------------------------------------------------------
+struct FastDim {
+    double hstep;  // step / 2
+    double tau;    // step * 2^-54
+    double lim;    // step * (1 - 2^-20)
+};
+
+__device__ __forceinline__ bool fast_cell(double x, double start, double step, double rstep, double lim, int dim,
+                                          int& origin, double& od, double& d) {
+    d = __dsub_rn(x, start);
+    const double q = __dmul_rn(d, rstep);
+    const int f = __double2int_rd(q);
+    origin = min(max(f, 0), dim - 2);
+    od = __int2double_rn(origin);
+    const double r = __fma_rn(-od, step, d);
+    const bool proven = r >= 0.0 && r <= lim;
+    const bool sane = static_cast<unsigned>(f) + (1u << 30) <= (1u << 31);
+    return origin == f ? proven : sane;
+}
+
+__device__ __forceinline__ bool nearest_upper(double e, double hstep, double tau) {
+    return !(__dsub_rn(e, hstep) <= tau);
+}
+
+__device__ __forceinline__ bool markstein_operand_ok(double a) {
+    const unsigned hi = static_cast<unsigned>(__double2hiint(a));
+    const unsigned e = (hi >> 20) & 0x7ffu;
+    return (e - 723u <= 600u) || ((hi << 1 | static_cast<unsigned>(__double2loint(a))) == 0u);
+}
+
+__device__ __forceinline__ double markstein_div(double a, double b, double rb) {
+    const double q0 = __dmul_rn(a, rb);
+    const double e0 = __fma_rn(-q0, b, a);
+    const double q1 = __fma_rn(e0, rb, q0);
+    const double e1 = __fma_rn(-q1, b, a);
+    return copysign(__fma_rn(e1, rb, q1), a);
 }
 
 // ref: multicubic/mod.rs:72-91 (strict arithmetic)

@@ -20,11 +20,13 @@ struct EvalArgs {
     const T* vals;
     const T* win;  // window layout of vals (see load_row), or nullptr
     long long stride[N];
+    int istride[N];  // the same strides when the grid has fewer than 2^31 values (32-bit index arithmetic), else 0
     int dim[N];
     T start[N];  // regular
     T step[N];   // regular
     T rstep[N];  // regular: RN(1/step), for exact_div
     int fast_div;  // regular: every step is within exact_div's exponent range
+    double hstep[N], tau[N], lim[N];  // regular f64: step/2, step*2^-54, step*(1-2^-20) (device_math.cuh fast_cell)
     const T* axes;    // rectilinear: packed axes (global)
     int axis_off[N];  // rectilinear
     int axes_total;   // rectilinear
@@ -35,6 +37,14 @@ struct EvalArgs {
 };
 
 constexpr int kBlock = 256;
+
+// Index arithmetic of the streaming kernels is 32-bit whenever the grid has fewer than 2^31 values
+// (I = int); the 64-bit variants (I = long long) cover everything else.
+template <class I, class T, int N>
+__device__ __forceinline__ const I (&strides_of(const EvalArgs<T, N>& a))[N] {
+    if constexpr (sizeof(I) == 4) return a.istride;
+    else return a.stride;
+}
 
 // Stage the packed rectilinear axes into dynamic shared memory (returns the pointer to search).
 template <class T, int N>
@@ -59,16 +69,15 @@ __device__ __forceinline__ void report_bad(unsigned long long* first_bad, unsign
 // that straddle two sectors 75 % (W=4) of the time.
 // ---------------------------------------------------------------------------------------------
 
-template <class T, int W, bool WIN>
-__device__ __forceinline__ void load_row(const T* __restrict__ vals, const T* __restrict__ win, long long idx,
-                                         T (&r)[W]) {
+template <class T, int W, bool WIN, class I = long long>
+__device__ __forceinline__ void load_row(const T* __restrict__ vals, const T* __restrict__ win, I idx, T (&r)[W]) {
     if constexpr (!WIN) {
 #pragma unroll
         for (int j = 0; j < W; ++j) r[j] = __ldg(vals + idx + j);
     } else if constexpr (sizeof(T) == 8 && W == 4) {
         asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
             : "=d"(r[0]), "=d"(r[1]), "=d"(r[2]), "=d"(r[3])
-            : "l"(win + idx * 4));
+            : "l"(win + static_cast<long long>(idx) * 4));
     } else if constexpr (sizeof(T) == 8 && W == 2) {
         double2 q = __ldg(reinterpret_cast<const double2*>(win) + idx);
         r[0] = q.x; r[1] = q.y;
@@ -129,16 +138,16 @@ __device__ __forceinline__ void store_result_vec(T* p, const T (&v)[P]) {
 // Reduces dimensions 0..D-1 of the sub-block at flat index `idx` for both positions of the last
 // (contiguous) dimension at once. Each lerp is the reference's `y0 + t*(y1 - y0)` with dimension 0
 // innermost, so every output is bit-identical to the reference's tree; only the load schedule differs.
-template <int D, class T, int N, bool WIN>
-__device__ __forceinline__ void linear_rows(const T* __restrict__ vals, const T* __restrict__ win, long long idx,
-                                            const long long (&stride)[N], const T (&t)[N], T (&out)[2]) {
+template <int D, class T, int N, bool WIN, class I>
+__device__ __forceinline__ void linear_rows(const T* __restrict__ vals, const T* __restrict__ win, I idx,
+                                            const I (&stride)[N], const T (&t)[N], T (&out)[2]) {
     using O = Ops<T>;
     if constexpr (D == 0) {
-        load_row<T, 2, WIN>(vals, win, idx, out);
+        load_row<T, 2, WIN, I>(vals, win, idx, out);
     } else {
         T lo[2], hi[2];
-        linear_rows<D - 1, T, N, WIN>(vals, win, idx, stride, t, lo);
-        linear_rows<D - 1, T, N, WIN>(vals, win, idx + stride[D - 1], stride, t, hi);
+        linear_rows<D - 1, T, N, WIN, I>(vals, win, idx, stride, t, lo);
+        linear_rows<D - 1, T, N, WIN, I>(vals, win, idx + stride[D - 1], stride, t, hi);
 #pragma unroll
         for (int j = 0; j < 2; ++j) out[j] = O::add(lo[j], O::mul(t[D - 1], O::sub(hi[j], lo[j])));
     }
@@ -146,9 +155,10 @@ __device__ __forceinline__ void linear_rows(const T* __restrict__ vals, const T*
 
 // Locate one query point: per-dimension cell origin -> flat index of the footprint's first corner,
 // and the normalized coordinates t. Returns false for an unrepresentable coordinate (regular grids).
-template <class T, int N, bool RECT>
+template <class T, int N, bool RECT, class I>
 __device__ __forceinline__ bool linear_locate(const EvalArgs<T, N>& a, const T* __restrict__ axes, const T (&xs)[N],
-                                              T (&t)[N], long long& base) {
+                                              T (&t)[N], I& base) {
+    const I(&stride)[N] = strides_of<I>(a);
     using O = Ops<T>;
     bool ok = true;
     base = 0;
@@ -169,15 +179,16 @@ __device__ __forceinline__ bool linear_locate(const EvalArgs<T, N>& a, const T* 
             T x0 = O::add(a.start[d], O::mul(a.step[d], O::from_int(origin)));
             t[d] = exact_div(O::sub(x, x0), a.step[d], a.rstep[d], a.fast_div != 0);
         }
-        base += static_cast<long long>(origin) * a.stride[d];
+        base += static_cast<I>(origin) * stride[d];
     }
     return ok;
 }
 
 // Nearest: flat index of the chosen node (ref: nearest/regular.rs:259-293, nearest/rectilinear.rs:213-239).
-template <class T, int N, bool RECT>
+template <class T, int N, bool RECT, class I>
 __device__ __forceinline__ bool nearest_locate(const EvalArgs<T, N>& a, const T* __restrict__ axes, const T (&xs)[N],
-                                               long long& idx) {
+                                               I& idx) {
+    const I(&stride)[N] = strides_of<I>(a);
     using O = Ops<T>;
     const T half = T(0.5);
     bool ok = true;
@@ -201,9 +212,68 @@ __device__ __forceinline__ bool nearest_locate(const EvalArgs<T, N>& a, const T*
             dt = exact_div(O::sub(x, x0), a.step[d], a.rstep[d], a.fast_div != 0);
         }
         const int off = (dt <= half) ? 0 : 1;  // tie -> lower index; NaN (rectilinear only) -> upper
-        idx += static_cast<long long>(origin + off) * a.stride[d];
+        idx += static_cast<I>(origin + off) * stride[d];
     }
     return ok;
+}
+
+// Division-free twins of linear_locate / nearest_locate for regular f64 grids (device_math.cuh
+// fast_cell & co.). They return false when a point needs the exact path; `base` / `idx` stay in range
+// either way.
+template <int N, class I>
+__device__ __forceinline__ bool linear_locate_fast(const EvalArgs<double, N>& a, const double (&xs)[N], double (&t)[N],
+                                                   I& base) {
+    const I(&stride)[N] = strides_of<I>(a);
+    bool sure = a.fast_div != 0;
+    base = 0;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+        int origin;
+        double od, dd;
+        sure = fast_cell(xs[d], a.start[d], a.step[d], a.rstep[d], a.lim[d], a.dim[d], origin, od, dd) && sure;
+        const double x0 = __dadd_rn(a.start[d], __dmul_rn(a.step[d], od));
+        const double e = __dsub_rn(xs[d], x0);
+        sure = markstein_operand_ok(e) && sure;
+        t[d] = markstein_div(e, a.step[d], a.rstep[d]);
+        base += static_cast<I>(origin) * stride[d];
+    }
+    return sure;
+}
+
+template <int N, class I>
+__device__ __forceinline__ bool nearest_locate_fast(const EvalArgs<double, N>& a, const double (&xs)[N], I& idx) {
+    const I(&stride)[N] = strides_of<I>(a);
+    bool sure = a.fast_div != 0;
+    idx = 0;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+        int origin;
+        double od, dd;
+        sure = fast_cell(xs[d], a.start[d], a.step[d], a.rstep[d], a.lim[d], a.dim[d], origin, od, dd) && sure;
+        const double x0 = __dadd_rn(a.start[d], __dmul_rn(a.step[d], od));
+        const double e = __dsub_rn(xs[d], x0);
+        const int off = nearest_upper(e, a.hstep[d], a.tau[d]) ? 1 : 0;
+        idx += static_cast<I>(origin + off) * stride[d];
+    }
+    return sure;
+}
+
+// One point of the streaming kernels: fast path where it exists, exact path otherwise.
+template <class T, int N, bool RECT, class I>
+__device__ __forceinline__ bool linear_locate_any(const EvalArgs<T, N>& a, const T* __restrict__ axes, const T (&xs)[N],
+                                                  T (&t)[N], I& base) {
+    if constexpr (!RECT && sizeof(T) == 8) {
+        if (linear_locate_fast<N, I>(a, xs, t, base)) return true;
+    }
+    return linear_locate<T, N, RECT, I>(a, axes, xs, t, base);
+}
+template <class T, int N, bool RECT, class I>
+__device__ __forceinline__ bool nearest_locate_any(const EvalArgs<T, N>& a, const T* __restrict__ axes, const T (&xs)[N],
+                                                   I& idx) {
+    if constexpr (!RECT && sizeof(T) == 8) {
+        if (nearest_locate_fast<N, I>(a, xs, idx)) return true;
+    }
+    return nearest_locate<T, N, RECT, I>(a, axes, xs, idx);
 }
 
 // The streaming kernels (multilinear, nearest) are a chain  DRAM load -> locate -> gather -> store
@@ -212,9 +282,10 @@ __device__ __forceinline__ bool nearest_locate(const EvalArgs<T, N>& a, const T*
 // coordinate array, P independent locate/gather chains in flight, one vector store. The host picks
 // P > 1 only when every coordinate array and `out` are P*sizeof(T)-aligned (launch_common.cuh); the
 // n % P tail is evaluated one point per thread.
-template <class T, int N, bool RECT, bool WIN, int P>
+template <class T, int N, bool RECT, bool WIN, int P, class I>
 __global__ void __launch_bounds__(kBlock) linear_kernel(const __grid_constant__ EvalArgs<T, N> a) {
     using O = Ops<T>;
+    const I(&stride)[N] = strides_of<I>(a);
     const T* axes = nullptr;
     if constexpr (RECT) axes = stage_axes<T, N>(a);
     const unsigned long long gstride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
@@ -236,12 +307,12 @@ __global__ void __launch_bounds__(kBlock) linear_kernel(const __grid_constant__ 
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             T t[N];
-            long long base;
-            ok[p] = linear_locate<T, N, RECT>(a, axes, xs[p], t, base);
+            I base;
+            ok[p] = linear_locate_any<T, N, RECT, I>(a, axes, xs[p], t, base);
             all_ok = all_ok && ok[p];
             if (!ok[p]) base = 0;  // keep the gather in range; the value is discarded
             T r[2];
-            linear_rows<N - 1, T, N, WIN>(a.vals, a.win, base, a.stride, t, r);
+            linear_rows<N - 1, T, N, WIN, I>(a.vals, a.win, base, stride, t, r);
             res[p] = O::add(r[0], O::mul(t[N - 1], O::sub(r[1], r[0])));
         }
         if (all_ok) {
@@ -261,10 +332,10 @@ __global__ void __launch_bounds__(kBlock) linear_kernel(const __grid_constant__ 
 #pragma unroll
             for (int d = 0; d < N; ++d) xs[d] = load_query(a.obs[d] + i);
             T t[N];
-            long long base;
-            if (linear_locate<T, N, RECT>(a, axes, xs, t, base)) {
+            I base;
+            if (linear_locate_any<T, N, RECT, I>(a, axes, xs, t, base)) {
                 T r[2];
-                linear_rows<N - 1, T, N, WIN>(a.vals, a.win, base, a.stride, t, r);
+                linear_rows<N - 1, T, N, WIN, I>(a.vals, a.win, base, stride, t, r);
                 store_result(a.out + i, O::add(r[0], O::mul(t[N - 1], O::sub(r[1], r[0]))));
             } else {
                 report_bad(a.first_bad, a.index_base + i);
@@ -277,7 +348,7 @@ __global__ void __launch_bounds__(kBlock) linear_kernel(const __grid_constant__ 
 // Nearest (ref: nearest/regular.rs:234-295, nearest/rectilinear.rs:193-241)
 // ---------------------------------------------------------------------------------------------
 
-template <class T, int N, bool RECT, int P>
+template <class T, int N, bool RECT, int P, class I>
 __global__ void __launch_bounds__(kBlock) nearest_kernel(const __grid_constant__ EvalArgs<T, N> a) {
     const T* axes = nullptr;
     if constexpr (RECT) axes = stage_axes<T, N>(a);
@@ -294,12 +365,12 @@ __global__ void __launch_bounds__(kBlock) nearest_kernel(const __grid_constant__
 #pragma unroll
             for (int p = 0; p < P; ++p) xs[p][d] = v[p];
         }
-        long long idx[P];
+        I idx[P];
         bool ok[P];
         bool all_ok = true;
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-            ok[p] = nearest_locate<T, N, RECT>(a, axes, xs[p], idx[p]);
+            ok[p] = nearest_locate_any<T, N, RECT, I>(a, axes, xs[p], idx[p]);
             all_ok = all_ok && ok[p];
             if (!ok[p]) idx[p] = 0;
         }
@@ -322,8 +393,8 @@ __global__ void __launch_bounds__(kBlock) nearest_kernel(const __grid_constant__
             T xs[N];
 #pragma unroll
             for (int d = 0; d < N; ++d) xs[d] = load_query(a.obs[d] + i);
-            long long idx;
-            if (nearest_locate<T, N, RECT>(a, axes, xs, idx)) store_result(a.out + i, __ldg(a.vals + idx));
+            I idx;
+            if (nearest_locate_any<T, N, RECT, I>(a, axes, xs, idx)) store_result(a.out + i, __ldg(a.vals + idx));
             else report_bad(a.first_bad, a.index_base + i);
         }
     }

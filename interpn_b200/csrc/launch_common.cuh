@@ -16,6 +16,7 @@ inline EvalArgs<T, N> make_args(const DeviceGrid& g, const T* const* obs, size_t
     for (int d = 0; d < N; ++d) {
         a.obs[d] = obs[d];
         a.stride[d] = g.stride[d];
+        a.istride[d] = g.nvals < (size_t(1) << 31) ? static_cast<int>(g.stride[d]) : 0;
         a.dim[d] = g.dim[d];
         a.start[d] = static_cast<T>(g.start[d]);
         a.step[d] = static_cast<T>(g.step[d]);
@@ -31,7 +32,12 @@ inline EvalArgs<T, N> make_args(const DeviceGrid& g, const T* const* obs, size_t
         // exact_div's divisor guard (device_math.cuh): 2^-300 <= step < 2^301 on every dimension
         a.fast_div = 1;
         for (int d = 0; d < N; ++d)
-            if (!(g.step[d] >= 0x1p-300 && g.step[d] < 0x1p301)) a.fast_div = 0;
+            if (!(g.step[d] >= 0x1p-300 && g.step[d] < 0x1p301) || g.dim[d] >= (1 << 30)) a.fast_div = 0;
+    }
+    for (int d = 0; d < N; ++d) {  // exact: power-of-two scalings of a step in the guarded range
+        a.hstep[d] = g.step[d] * 0.5;
+        a.tau[d] = g.step[d] * 0x1p-54;
+        a.lim[d] = g.step[d] * (1.0 - 0x1p-20);
     }
     a.axes = static_cast<const T*>(g.axes);
     a.axes_total = g.axes_total;

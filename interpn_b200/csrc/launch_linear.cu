@@ -7,9 +7,11 @@ template <class T, int N, bool RECT, bool WIN>
 cudaError_t launch_linear_n(const DeviceGrid& g, const T* const* obs, size_t n, T* out, unsigned long long* first_bad,
                             unsigned long long index_base, cudaStream_t stream) {
     constexpr int P = linear_points_per_thread<N>();
+    if (g.nvals >= (size_t(1) << 31))  // 64-bit index arithmetic: the basic kernel only
+        return launch_generic<T, N>(linear_kernel<T, N, RECT, false, 1, long long>, g, obs, n, out, first_bad, index_base, stream);
     if (P > 1 && n >= static_cast<size_t>(P) && vector_aligned<T>(obs, N, out, P))
-        return launch_generic<T, N>(linear_kernel<T, N, RECT, WIN, P>, g, obs, n, out, first_bad, index_base, stream, P);
-    return launch_generic<T, N>(linear_kernel<T, N, RECT, WIN, 1>, g, obs, n, out, first_bad, index_base, stream);
+        return launch_generic<T, N>(linear_kernel<T, N, RECT, WIN, P, int>, g, obs, n, out, first_bad, index_base, stream, P);
+    return launch_generic<T, N>(linear_kernel<T, N, RECT, WIN, 1, int>, g, obs, n, out, first_bad, index_base, stream);
 }
 
 template <class T>

@@ -1,0 +1,135 @@
+// numeric_tricks.cpp — CPU re-check of the three division-avoiding sequences of
+// interpn_b200/csrc/device_math.cuh (markstein_div / exact_div, fast_cell, nearest_upper) against
+// the IEEE operations the reference performs. Test infrastructure: compiled and run by
+// tests/test_numeric_tricks.py with g++ -O2 -ffp-contract=off (std::fma is a single rounding).
+//
+// Usage: numeric_tricks <millions of random trials>; prints "OK <trials>" or the first counterexample.
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+static uint64_t s_state = 0x243F6A8885A308D3ull;
+static inline uint64_t rnd() {
+    uint64_t z = (s_state += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+static inline double u01() { return (rnd() >> 11) * (1.0 / 9007199254740992.0); }
+static inline uint64_t bits(double x) { uint64_t b; memcpy(&b, &x, 8); return b; }
+static inline double from_bits(uint64_t b) { double x; memcpy(&x, &b, 8); return x; }
+static inline double nudge(double x, int k) { return from_bits(bits(x) + (int64_t)k); }  // k ulps (same sign/exponent region)
+
+// ---- device_math.cuh restated with host operations -------------------------------------------
+static inline bool operand_ok(double a) {
+    const uint64_t b = bits(a);
+    const unsigned hi = (unsigned)(b >> 32), lo = (unsigned)b;
+    const unsigned e = (hi >> 20) & 0x7ffu;
+    return (e - 723u <= 600u) || ((hi << 1 | lo) == 0u);
+}
+static inline double markstein_div(double a, double b, double rb) {
+    const double q0 = a * rb;
+    const double e0 = std::fma(-q0, b, a);
+    const double q1 = std::fma(e0, rb, q0);
+    const double e1 = std::fma(-q1, b, a);
+    return std::copysign(std::fma(e1, rb, q1), a);
+}
+static inline int floor_sat(double q) {  // F2I.S32.F64.FLOOR: saturating, NaN -> 0
+    if (q != q) return 0;
+    double f = std::floor(q);
+    if (f >= 2147483647.0) return 2147483647;
+    if (f <= -2147483648.0) return (int)-2147483648ll;
+    return (int)f;
+}
+static inline bool fast_cell(double x, double start, double step, double rstep, double lim, int dim, int& origin,
+                             double& od, double& d) {
+    d = x - start;
+    const double q = d * rstep;
+    const int f = floor_sat(q);
+    int o = f < 0 ? 0 : f;
+    origin = o > dim - 2 ? dim - 2 : o;
+    od = (double)origin;
+    const double r = std::fma(-od, step, d);
+    const bool proven = r >= 0.0 && r <= lim;
+    const bool sane = (unsigned)f + (1u << 30) <= (1u << 31);
+    return origin == f ? proven : sane;
+}
+static inline bool nearest_upper(double e, double hstep, double tau) { return !((e - hstep) <= tau); }
+
+// ---- the reference's operations (multilinear/regular.rs:414-425, nearest/regular.rs:259-293) ---
+static inline bool ref_cell(double x, double start, double step, int dim, int& origin) {
+    const double q = std::floor((x - start) / step);
+    if (!(q >= -9223372036854775808.0 && q < 9223372036854775808.0)) return false;
+    long long i = (long long)q;
+    long long o = i < 0 ? 0 : i;
+    origin = (int)(o > dim - 2 ? dim - 2 : o);
+    return true;
+}
+
+#define FAIL(...) do { printf(__VA_ARGS__); printf("\n"); return 1; } while (0)
+
+int main(int argc, char** argv) {
+    const long trials = (argc > 1 ? atol(argv[1]) : 20) * 1000000L;
+    long checked = 0;
+    for (long it = 0; it < trials; ++it) {
+        // a grid: step over ~60 binades, start over a wide range, a few hundred nodes
+        const double step = std::ldexp(0.5 + u01(), (int)(rnd() % 61) - 30);
+        const double rstep = 1.0 / step;
+        const double start = (u01() - 0.5) * std::ldexp(1.0, (int)(rnd() % 40) - 10);
+        const int dim = 2 + (int)(rnd() % 300);
+        const double hstep = step * 0.5, tau = step * 0x1p-54, lim = step * (1.0 - 0x1p-20);
+        // a query: uniform over the grid +-30 %, or planted on / next to a node, or next to a mid-point
+        const int k = (int)(rnd() % (unsigned)dim);
+        double x;
+        switch (rnd() % 6) {
+            case 0: x = start + step * (double)k; break;                                   // the node as the kernels compute it
+            case 1: x = nudge(start + step * (double)k, (int)(rnd() % 9) - 4); break;      // within 4 ulps of a node
+            case 2: x = nudge(start + step * (double)k + hstep, (int)(rnd() % 9) - 4); break;  // around the nearest tie
+            case 3: x = nudge((start + step * (double)k) + hstep, (int)(rnd() % 5) - 2); break;
+            default: x = start + step * (double)(dim - 1) * (1.6 * u01() - 0.3); break;
+        }
+        int o_ref, o_fast;
+        double od, d;
+        const bool ref_ok = ref_cell(x, start, step, dim, o_ref);
+        const bool sure = fast_cell(x, start, step, rstep, lim, dim, o_fast, od, d);
+        if (sure) {
+            if (!ref_ok || o_ref != o_fast)
+                FAIL("fast_cell: x=%a start=%a step=%a dim=%d ref=%d fast=%d", x, start, step, dim, o_ref, o_fast);
+            const double x0 = start + step * od;
+            const double e = x - x0;
+            const bool up_ref = !((e / step) <= 0.5);
+            if (nearest_upper(e, hstep, tau) != up_ref) FAIL("nearest_upper: e=%a step=%a", e, step);
+            if (operand_ok(e)) {
+                const double t_ref = e / step, t = markstein_div(e, step, rstep);
+                if (bits(t) != bits(t_ref)) FAIL("markstein t: e=%a step=%a got=%a want=%a", e, step, t, t_ref);
+            }
+            ++checked;
+        }
+        // general operands for the division itself (cubic rectilinear spacing ratios reuse it)
+        const double b = std::ldexp(0.5 + u01(), (int)(rnd() % 400) - 200);
+        double a = std::ldexp(u01() - 0.5, (int)(rnd() % 400) - 200);
+        if (rnd() % 8 == 0) a = nudge(b * (double)(rnd() % 1000), (int)(rnd() % 5) - 2);  // near-exact quotients
+        if (rnd() % 64 == 0) a = (rnd() & 1) ? 0.0 : -0.0;
+        if (operand_ok(a)) {
+            const double w = a / b, g = markstein_div(a, b, 1.0 / b);
+            if (bits(w) != bits(g)) FAIL("markstein_div: a=%a b=%a got=%a want=%a", a, b, g, w);
+        }
+    }
+    // exhaustive neighbourhood of the tie for a few steps: e = step/2 + k ulps, k = -64..64
+    const double steps[] = {1.0, 0.1, 100.0 / 99.0, 0.125, 3.0, 1e-7, 12345.678, 0x1.fffffffffffffp+3, 0x1.0000000000001p-5};
+    for (double step : steps)
+        for (int k = -64; k <= 64; ++k) {
+            const double e = nudge(step * 0.5, k);
+            if (nearest_upper(e, step * 0.5, step * 0x1p-54) != !((e / step) <= 0.5)) FAIL("tie sweep: e=%a step=%a", e, step);
+        }
+    // special values never pass the fast path
+    const double specials[] = {NAN, INFINITY, -INFINITY, 1e300, -1e300, 0x1p62, -0x1p62};
+    for (double x : specials) {
+        int o; double od, d;
+        if (fast_cell(x, 0.0, 1e-3, 1e3, 1e-3 * (1.0 - 0x1p-20), 10, o, od, d)) FAIL("special value %a passed fast_cell", x);
+    }
+    printf("OK %ld %ld\n", trials, checked);
+    return 0;
+}

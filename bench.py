@@ -298,6 +298,7 @@ def run_b200(args):
         dist.barrier()
         torch.cuda.synchronize()
     launches0 = ib.launch_count()
+    swept0 = ib.swept_launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     with ClockSampler(local_rank) as clocks:
         ev[0].record(stream)
@@ -308,6 +309,7 @@ def run_b200(args):
     if distributed:
         dist.barrier()
     launches = ib.launch_count() - launches0
+    swept = ib.swept_launch_count() - swept0
     interp.status(stream.cuda_stream)
     total_ms = ev[0].elapsed_time(ev[-1])
     step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
@@ -416,6 +418,7 @@ def run_b200(args):
         "roofline": roofline,
         "e2e": e2e,
         "gpu_launches": int(launches),
+        "swept_launches": int(swept),
         "clocks": clocks.summary(),
         "parity": parity,
         "setup_s": setup_s,

@@ -90,6 +90,8 @@ int interpn_b200_device_count(void);
 int interpn_b200_set_device(int device);
 /* Number of kernels this library has launched in this process (all threads); bench.py reports the delta. */
 uint64_t interpn_b200_launch_count(void);
+/* How many of those launches were bin-swept evaluations (grids beyond L2, interpn_b200/csrc/sweep.cuh). */
+uint64_t interpn_b200_swept_launch_count(void);
 /* Streaming multiprocessors of the current device (148 on B200); 0 when there is no device. */
 int interpn_b200_sm_count(void);
 

@@ -16,7 +16,7 @@ There is no CPU fallback: importing fails without the built library and compute 
 from __future__ import annotations
 
 from . import _lib, one_dim, raw
-from ._lib import InterpnDeviceError, device_count, launch_count, set_device
+from ._lib import InterpnDeviceError, device_count, launch_count, set_device, swept_launch_count
 from .interpolator import Interpolator
 from .api import (
     MulticubicRectilinear,
@@ -46,4 +46,5 @@ __all__ = [
     "device_count",
     "launch_count",
     "set_device",
+    "swept_launch_count",
 ]

@@ -44,6 +44,7 @@ def _load() -> C.CDLL:
     lib.interpn_b200_strerror.argtypes = [C.c_int]
     lib.interpn_b200_last_error_detail.restype = C.c_char_p
     lib.interpn_b200_launch_count.restype = C.c_uint64
+    lib.interpn_b200_swept_launch_count.restype = C.c_uint64
     lib.interpn_b200_interp_vals_ptr.restype = C.c_void_p
     lib.interpn_b200_interp_vals_ptr.argtypes = [C.c_void_p]
     for name in ("interpn_b200_interp_vals_len", "interpn_b200_interp_elem_size", "interpn_b200_interp_ndims"):
@@ -78,6 +79,10 @@ def check(status: int) -> None:
 
 def launch_count() -> int:
     return int(lib.interpn_b200_launch_count())
+
+
+def swept_launch_count() -> int:
+    return int(lib.interpn_b200_swept_launch_count())
 
 
 def device_count() -> int:

@@ -20,6 +20,8 @@ namespace ib200 {
 
 static std::atomic<uint64_t> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+static std::atomic<uint64_t> g_swept{0};
+void count_swept_launch() { g_swept.fetch_add(1, std::memory_order_relaxed); }
 
 static thread_local char t_detail[512] = "";
 
@@ -268,10 +270,19 @@ int window_width(const DeviceGrid& g) {
     if (g.method == INTERPN_B200_LINEAR && g.ndims <= 6) w = 2;
     if (g.method == INTERPN_B200_CUBIC && g.ndims <= 4) w = 4;
     if (!w) return 0;
-    size_t max_mb = 64;
+    // Kept up to 8 GiB and a quarter of the free memory. Direct kernels gather from it only while it is
+    // L2-resident (<= 64 MB, launch_common.cuh kWindowL2Bytes); beyond that it serves the bin-swept path
+    // (sweep.cuh), where the slab being gathered from is L2-resident and a row is one L1 wavefront.
+    size_t max_mb = 8192;
     if (const char* e = getenv("INTERPN_B200_WINDOW_MB")) max_mb = static_cast<size_t>(strtoull(e, nullptr, 10));
     const size_t bytes = g.nvals * static_cast<size_t>(g.elem);
-    if (bytes < (size_t(128) << 10) || bytes * w > (max_mb << 20)) return 0;
+    size_t min_kb = 128;  // smaller grids live in L1 anyway
+    if (const char* e = getenv("INTERPN_B200_WINDOW_MIN_KB")) min_kb = static_cast<size_t>(strtoull(e, nullptr, 10));
+    if (bytes < (min_kb << 10) || bytes * w > (max_mb << 20)) return 0;
+    if (bytes * w > (size_t(64) << 20)) {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || bytes * w > free_b / 4) return 0;
+    }
     return w;
 }
 
@@ -280,6 +291,7 @@ int upload_vals(interpn_b200_interp* h, const void* vals, int vals_location) {
     const size_t bytes = g.nvals * static_cast<size_t>(g.elem);
     CUDA_TRY(cudaMalloc(&g.vals, bytes ? bytes : 1));
     g.win_width = window_width(g);
+    g.win_cross = g.win_width == 4 && g.ndims >= 2;  // cubic N = 2..4: quad-cooperative kernels
     if (g.win_width) CUDA_TRY(cudaMalloc(&g.win, bytes * g.win_width));
     if (vals_location == INTERPN_B200_VALS_UNINIT) return INTERPN_B200_OK;
     if (!vals) return INTERPN_B200_ERR_INVALID_ARG;
@@ -292,6 +304,13 @@ int upload_vals(interpn_b200_interp* h, const void* vals, int vals_location) {
 
 int finish_new(interpn_b200_interp* h) {
     CUDA_TRY(cudaGetDevice(&h->device));
+    // The bin-swept kernels take their scratch from the stream-ordered default pool: keep it cached.
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
     CUDA_TRY(cudaMalloc(&h->first_bad_dev, sizeof(unsigned long long)));
     CUDA_TRY(cudaMemset(h->first_bad_dev, 0xff, sizeof(unsigned long long)));
     return INTERPN_B200_OK;
@@ -653,6 +672,7 @@ int interpn_b200_set_device(int device) {
 }
 
 uint64_t interpn_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+uint64_t interpn_b200_swept_launch_count(void) { return g_swept.load(std::memory_order_relaxed); }
 
 int interpn_b200_sm_count(void) {
     int sms = 0;

@@ -26,6 +26,7 @@ struct DeviceGrid {
     // (linear) or 4 (cubic). Present only for mid-size grids (window_policy in capi.cu).
     void* win = nullptr;
     int win_width = 0;
+    int win_cross = 0;         // cubic, N = 2..4: the cross-window layout of kernels.cuh cubic_quad_point
     void* axes = nullptr;           // device, all rectilinear axes packed back to back
     int axis_off[kMaxNd] = {};      // element offset of axis d inside `axes`
     int axes_total = 0;
@@ -52,5 +53,6 @@ cudaError_t launch_check_bounds(const T* x, size_t n, T lo, T hi, T atol, int* f
 cudaError_t launch_build_window(const DeviceGrid& g, cudaStream_t stream);
 
 void count_launch();
+void count_swept_launch();
 
 }  // namespace ib200

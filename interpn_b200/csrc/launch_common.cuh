@@ -11,8 +11,11 @@ constexpr int kAxesSmemBudget = 96 * 1024;
 
 template <class T, int N>
 inline EvalArgs<T, N> make_args(const DeviceGrid& g, const T* const* obs, size_t n, T* out,
-                                unsigned long long* first_bad, unsigned long long index_base) {
+                                unsigned long long* first_bad, unsigned long long index_base,
+                                const unsigned* remap = nullptr, unsigned long long* work = nullptr) {
     EvalArgs<T, N> a{};
+    a.remap = remap;
+    a.work = work;
     for (int d = 0; d < N; ++d) {
         a.obs[d] = obs[d];
         a.stride[d] = g.stride[d];
@@ -82,22 +85,25 @@ constexpr int linear_points_per_thread() {
 template <class T, int N, class K>
 inline cudaError_t launch_generic(K kernel, const DeviceGrid& g, const T* const* obs, size_t n, T* out,
                                   unsigned long long* first_bad, unsigned long long index_base, cudaStream_t stream,
-                                  int points_per_thread = 1, int ctas_per_sm = 8) {
+                                  int points_per_thread = 1, const unsigned* remap = nullptr,
+                                  unsigned long long* work = nullptr, int threads_per_point = 1, int ctas_per_sm = 8) {
     if (n == 0) return cudaSuccess;
-    EvalArgs<T, N> a = make_args<T, N>(g, obs, n, out, first_bad, index_base);
+    EvalArgs<T, N> a = make_args<T, N>(g, obs, n, out, first_bad, index_base, remap, work);
     size_t smem = a.axes_in_smem ? static_cast<size_t>(g.axes_total) * sizeof(T) : 0;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
     }
-    const size_t work = (n + points_per_thread - 1) / points_per_thread;
-    kernel<<<grid_for(work, g.sm_count, ctas_per_sm), kBlock, smem, stream>>>(a);
+    const size_t items = (n + points_per_thread - 1) / points_per_thread * threads_per_point;
+    kernel<<<grid_for(items, g.sm_count, ctas_per_sm), kBlock, smem, stream>>>(a);
     count_launch();
     return cudaGetLastError();
 }
 
 // Window-layout kernels are instantiated up to these dimensionalities (interp_internal.h mirrors them
 // in window_policy): the cubic footprint is unrolled row by row only in the flattened range N <= 4.
+// A window copy no larger than this is treated as L2-resident by the direct kernels.
+constexpr size_t kWindowL2Bytes = size_t(64) << 20;
 constexpr int kMaxWindowDimsLinear = 6;
 constexpr int kMaxWindowDimsCubic = 4;
 
@@ -115,6 +121,19 @@ constexpr int kMaxWindowDimsCubic = 4;
 #endif
 #ifndef IB200_MINB_CUBIC4_RECT
 #define IB200_MINB_CUBIC4_RECT 3
+#endif
+// Quad-cooperative kernels (kernels.cuh cubic_quad_kernel): resident CTAs per SM the register budget must allow.
+#ifndef IB200_MINB_QUAD2
+#define IB200_MINB_QUAD2 3
+#endif
+#ifndef IB200_MINB_QUAD3
+#define IB200_MINB_QUAD3 4
+#endif
+#ifndef IB200_MINB_QUAD3_RECT
+#define IB200_MINB_QUAD3_RECT 2
+#endif
+#ifndef IB200_MINB_QUAD4
+#define IB200_MINB_QUAD4 2
 #endif
 template <int N, bool RECT>
 constexpr int cubic_min_blocks() {

@@ -1,5 +1,5 @@
 // launch_cubic_rect.cu — multicubic rectilinear-grid launchers (f32/f64, N = 1..8).
-#include "launch_common.cuh"
+#include "sweep.cuh"
 
 namespace ib200 {
 
@@ -7,11 +7,38 @@ template <class T>
 cudaError_t launch_cubic_rect(const DeviceGrid& g, const T* const* obs, size_t n, T* out,
                               unsigned long long* first_bad, unsigned long long index_base, cudaStream_t stream) {
     cudaError_t err = cudaErrorInvalidValue;
-    if (g.win != nullptr && g.win_width == 4 && g.ndims <= kMaxWindowDimsCubic) {
-        IB200_SWITCH_N(kMaxWindowDimsCubic, err = (launch_generic<T, N>(cubic_kernel<T, N, true, true, cubic_min_blocks<N, true>()>, g, obs, n, out, first_bad, index_base, stream));)
-    } else {
-        IB200_SWITCH_N(8, err = (launch_generic<T, N>(cubic_kernel<T, N, true, false, cubic_min_blocks<N, true>()>, g, obs, n, out, first_bad, index_base, stream));)
+    // Window copies (capi.cu window_width): plain for N = 1, cross-window for N = 2..4 (quad-cooperative kernels).
+    const bool has_win = g.win != nullptr && g.win_width == 4 && g.ndims <= kMaxWindowDimsCubic;
+    // `remap` / `work` are set by the bin-swept path, which runs the same kernels on sorted coordinates.
+    auto direct = [&](bool win, const T* const* o, size_t cnt, T* dst, unsigned long long base, const unsigned* remap,
+                      unsigned long long* work) {
+        cudaError_t e = cudaErrorInvalidValue;
+        if (win && g.ndims == 1) {
+            e = launch_generic<T, 1>(cubic_kernel<T, 1, true, true, 1>, g, o, cnt, dst, first_bad, base, stream, 1, remap, work);
+        } else if (win) {
+            switch (g.ndims) {
+                case 2: e = launch_generic<T, 2>(cubic_quad_kernel<T, 2, true, IB200_MINB_QUAD2>, g, o, cnt, dst, first_bad, base, stream, 1, remap, work, 4); break;
+                case 3: e = launch_generic<T, 3>(cubic_quad_kernel<T, 3, true, IB200_MINB_QUAD3_RECT>, g, o, cnt, dst, first_bad, base, stream, 1, remap, work, 4); break;
+                case 4: e = launch_generic<T, 4>(cubic_quad_kernel<T, 4, true, IB200_MINB_QUAD4>, g, o, cnt, dst, first_bad, base, stream, 1, remap, work, 4); break;
+                default: break;
+            }
+        } else {
+            IB200_SWITCH_N(8, e = (launch_generic<T, N>(cubic_kernel<T, N, true, false, cubic_min_blocks<N, true>()>, g, o, cnt, dst, first_bad, base, stream, 1, remap, work));)
+        }
+        return e;
+    };
+    // Grids beyond L2: bin-swept evaluation (sweep.cuh), gathering from the window layout when there is one.
+    if (g.ndims >= 2 && g.ndims <= kMaxWindowDimsCubic) {
+        bool swept = false;
+        auto eval = [&](const T* const* sobs, size_t cnt, T* res, const unsigned* orig, unsigned long long base,
+                        unsigned long long* work) {
+            return direct(has_win, sobs, cnt, res, base, orig, work);
+        };
+        IB200_SWITCH_N(kMaxWindowDimsCubic, if constexpr (N >= 2) err = (launch_sweep<T, N, true>(g, 4, has_win ? 4 : 1, 1 << (2 * (N - 1)), obs, n, out, first_bad, index_base, stream, eval, swept));)
+        if (err != cudaSuccess || swept) return err;
     }
+    // Direct kernels gather from the window layout only while it is L2-resident.
+    err = direct(has_win && g.nvals * sizeof(T) * 4 <= kWindowL2Bytes, obs, n, out, index_base, nullptr, nullptr);
     return err;
 }
 

@@ -1,36 +1,55 @@
 // launch_linear.cu — multilinear launchers (regular + rectilinear, f32/f64, N = 1..8).
-#include "launch_common.cuh"
+#include "sweep.cuh"
 
 namespace ib200 {
 
+// The ordinary (direct) kernels. `remap` is set by the bin-swept path, which runs them on sorted coordinates.
 template <class T, int N, bool RECT, bool WIN>
-cudaError_t launch_linear_n(const DeviceGrid& g, const T* const* obs, size_t n, T* out, unsigned long long* first_bad,
-                            unsigned long long index_base, cudaStream_t stream) {
+cudaError_t launch_linear_direct(const DeviceGrid& g, const T* const* obs, size_t n, T* out, unsigned long long* first_bad,
+                                 unsigned long long index_base, cudaStream_t stream, const unsigned* remap,
+                                 unsigned long long* work) {
     constexpr int P = linear_points_per_thread<N>();
     if (g.nvals >= (size_t(1) << 31))  // 64-bit index arithmetic: the basic kernel only
-        return launch_generic<T, N>(linear_kernel<T, N, RECT, false, 1, long long>, g, obs, n, out, first_bad, index_base, stream);
+        return launch_generic<T, N>(linear_kernel<T, N, RECT, false, 1, long long>, g, obs, n, out, first_bad, index_base, stream, 1, remap, work);
     if (P > 1 && n >= static_cast<size_t>(P) && vector_aligned<T>(obs, N, out, P))
-        return launch_generic<T, N>(linear_kernel<T, N, RECT, WIN, P, int>, g, obs, n, out, first_bad, index_base, stream, P);
-    return launch_generic<T, N>(linear_kernel<T, N, RECT, WIN, 1, int>, g, obs, n, out, first_bad, index_base, stream);
+        return launch_generic<T, N>(linear_kernel<T, N, RECT, WIN, P, int>, g, obs, n, out, first_bad, index_base, stream, P, remap, work);
+    return launch_generic<T, N>(linear_kernel<T, N, RECT, WIN, 1, int>, g, obs, n, out, first_bad, index_base, stream, 1, remap, work);
+}
+
+template <class T, int N, bool RECT>
+cudaError_t launch_linear_n(const DeviceGrid& g, const T* const* obs, size_t n, T* out, unsigned long long* first_bad,
+                            unsigned long long index_base, cudaStream_t stream) {
+    constexpr bool kCanWin = N <= kMaxWindowDimsLinear;
+    const bool has_win = kCanWin && g.win != nullptr && g.win_width == 2;
+    if constexpr (N >= 2) {  // grids beyond L2: bin-swept evaluation (sweep.cuh), from the window layout when there is one
+        bool swept = false;
+        cudaError_t e = launch_sweep<T, N, RECT>(
+            g, 2, has_win ? 2 : 1, 1 << (N - 1), obs, n, out, first_bad, index_base, stream,
+            [&](const T* const* sobs, size_t cnt, T* res, const unsigned* orig, unsigned long long base, unsigned long long* work) {
+                if constexpr (kCanWin) {
+                    if (has_win) return launch_linear_direct<T, N, RECT, true>(g, sobs, cnt, res, first_bad, base, stream, orig, work);
+                }
+                return launch_linear_direct<T, N, RECT, false>(g, sobs, cnt, res, first_bad, base, stream, orig, work);
+            },
+            swept);
+        if (e != cudaSuccess || swept) return e;
+    }
+    // Direct kernels gather from the window layout only while it is L2-resident.
+    if constexpr (kCanWin) {
+        if (has_win && g.nvals * sizeof(T) * 2 <= kWindowL2Bytes)
+            return launch_linear_direct<T, N, RECT, true>(g, obs, n, out, first_bad, index_base, stream, nullptr, nullptr);
+    }
+    return launch_linear_direct<T, N, RECT, false>(g, obs, n, out, first_bad, index_base, stream, nullptr, nullptr);
 }
 
 template <class T>
 cudaError_t launch_linear(const DeviceGrid& g, const T* const* obs, size_t n, T* out, unsigned long long* first_bad,
                           unsigned long long index_base, cudaStream_t stream) {
     cudaError_t err = cudaErrorInvalidValue;
-    const bool win = g.win != nullptr && g.win_width == 2 && g.ndims <= kMaxWindowDimsLinear;
     if (g.rect) {
-        if (win) {
-            IB200_SWITCH_N(kMaxWindowDimsLinear, err = (launch_linear_n<T, N, true, true>(g, obs, n, out, first_bad, index_base, stream));)
-        } else {
-            IB200_SWITCH_N(8, err = (launch_linear_n<T, N, true, false>(g, obs, n, out, first_bad, index_base, stream));)
-        }
+        IB200_SWITCH_N(8, err = (launch_linear_n<T, N, true>(g, obs, n, out, first_bad, index_base, stream));)
     } else {
-        if (win) {
-            IB200_SWITCH_N(kMaxWindowDimsLinear, err = (launch_linear_n<T, N, false, true>(g, obs, n, out, first_bad, index_base, stream));)
-        } else {
-            IB200_SWITCH_N(8, err = (launch_linear_n<T, N, false, false>(g, obs, n, out, first_bad, index_base, stream));)
-        }
+        IB200_SWITCH_N(8, err = (launch_linear_n<T, N, false>(g, obs, n, out, first_bad, index_base, stream));)
     }
     return err;
 }

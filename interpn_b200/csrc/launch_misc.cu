@@ -1,7 +1,14 @@
 // launch_misc.cu — one_dim evaluators, check_bounds, and the method dispatcher.
+#include <cstdlib>
+
 #include "launch_common.cuh"
 
 namespace ib200 {
+
+size_t sweep_env(const char* name, size_t fallback) {
+    const char* e = getenv(name);
+    return e && *e ? static_cast<size_t>(strtoull(e, nullptr, 10)) : fallback;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Window layout builder: win[f*W + j] = vals[min(f + j, nvals - 1)]  (kernels.cuh load_row)
@@ -19,9 +26,33 @@ __global__ void __launch_bounds__(kBlock) build_window_kernel(const T* __restric
     }
 }
 
+// Cross-window layout (kernels.cuh cubic_quad_point): xwin[f*4 + b] = vals[f + min(b, Da - 1 - i_a) * Db], where
+// a = N-2, b-dimension = N-1 and f is the flat C-order index.
+template <class T>
+__global__ void __launch_bounds__(kBlock) build_xwindow_kernel(const T* __restrict__ vals, T* __restrict__ xwin,
+                                                               unsigned long long nvals, unsigned long long da,
+                                                               unsigned long long db) {
+    const unsigned long long total = nvals * 4;
+    const unsigned long long gstride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+    for (unsigned long long k = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; k < total;
+         k += gstride) {
+        const unsigned long long f = k >> 2, b = k & 3;
+        const unsigned long long ia = (f / db) % da;
+        const unsigned long long bb = ia + b < da ? b : da - 1 - ia;
+        xwin[k] = vals[f + bb * db];
+    }
+}
+
 cudaError_t launch_build_window(const DeviceGrid& g, cudaStream_t stream) {
     if (!g.win || g.nvals == 0) return cudaSuccess;
     const unsigned grid_dim = grid_for(g.nvals * g.win_width, g.sm_count, 8);
+    if (g.win_cross) {
+        const unsigned long long da = g.dim[g.ndims - 2], db = g.dim[g.ndims - 1];
+        if (g.elem == 8) build_xwindow_kernel<double><<<grid_dim, kBlock, 0, stream>>>(static_cast<const double*>(g.vals), static_cast<double*>(g.win), g.nvals, da, db);
+        else build_xwindow_kernel<float><<<grid_dim, kBlock, 0, stream>>>(static_cast<const float*>(g.vals), static_cast<float*>(g.win), g.nvals, da, db);
+        count_launch();
+        return cudaGetLastError();
+    }
     if (g.elem == 8) {
         if (g.win_width == 4) build_window_kernel<double, 4><<<grid_dim, kBlock, 0, stream>>>(static_cast<const double*>(g.vals), static_cast<double*>(g.win), g.nvals);
         else build_window_kernel<double, 2><<<grid_dim, kBlock, 0, stream>>>(static_cast<const double*>(g.vals), static_cast<double*>(g.win), g.nvals);
@@ -73,7 +104,7 @@ __global__ void __launch_bounds__(kBlock) one_dim_kernel(const __grid_constant__
             else if (loc < a.start) extrap = kOutsideLow;
             int iloc = 0;
             if (!floor_cell(loc, a.start, a.step, a.step, false, iloc)) {
-                report_bad(a.first_bad, a.index_base + i);
+                atomicMin(a.first_bad, a.index_base + i);
                 continue;
             }
             cell = clamp_cell(iloc, a.nvals - 2);

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     import interpn_b200._lib as L
 
     names = declared_symbols()
-    assert len(names) == 41, sorted(names)
+    assert len(names) == 42, sorted(names)
     lib = ctypes.CDLL(L.LIB_PATH)
     missing = [n for n in sorted(names) if not hasattr(lib, n)]
     assert not missing, missing

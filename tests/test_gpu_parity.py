@@ -80,8 +80,17 @@ for _dtype in (np.float64, np.float32):
         CASES.append(("nearest", _n, _dtype))
 
 
+@pytest.mark.parametrize("layout", ["plain", "window"])
 @pytest.mark.parametrize("method,ndims,dtype", CASES, ids=lambda v: getattr(v, "__name__", str(v)))
-def test_random_grids_bit_exact(ib, oracle, method, ndims, dtype):
+def test_random_grids_bit_exact(ib, oracle, monkeypatch, method, ndims, dtype, layout):
+    """`window` forces the derived gather layouts (window copy for multilinear, transposed window +
+    quad-cooperative kernels for multicubic N = 2..4) onto these small grids; `plain` disables them."""
+    if layout == "window":
+        if method == "nearest" or ndims > (6 if method == "linear" else 4):
+            pytest.skip("no window layout for this method / dimensionality")
+        monkeypatch.setenv("INTERPN_B200_WINDOW_MIN_KB", "0")
+    else:
+        monkeypatch.setenv("INTERPN_B200_WINDOW_MB", "0")
     rng = np.random.default_rng(1000 * ndims + len(method))
     min_dim = 4 if method == "cubic" else 2
     max_dim = {1: 40, 2: 20, 3: 12, 4: 8, 5: 6, 6: 5, 7: 4, 8: 4}[ndims]
@@ -103,6 +112,53 @@ def test_random_grids_bit_exact(ib, oracle, method, ndims, dtype):
         fn(*args)
         want = oracle.interpn_rectilinear(method, grids, vals, obs, linearize_extrapolation=linearize, nthreads=4)
         assert_same_bits(out, want, f"{method} rectilinear N={ndims} {sfx} lin={linearize}")
+
+
+SWEEP_CASES = [("linear", n, dt) for dt in (np.float64, np.float32) for n in (2, 3, 4, 6, 8)] + [
+    ("cubic", n, dt) for dt in (np.float64, np.float32) for n in (2, 3, 4)
+]
+
+
+@pytest.mark.parametrize("method,ndims,dtype", SWEEP_CASES, ids=lambda v: getattr(v, "__name__", str(v)))
+def test_bin_swept_evaluation_bit_exact(ib, oracle, monkeypatch, method, ndims, dtype):
+    """The bin-swept kernels (sweep.cuh: grids beyond L2) forced onto small grids: tiny slabs so the key
+    spans several dimensions, tiny tiles so every CTA sorts several of them, a ragged last tile, and
+    unrepresentable points in the middle of the batch."""
+    monkeypatch.setenv("INTERPN_B200_SWEEP_MIN_MB", "0")
+    monkeypatch.setenv("INTERPN_B200_SWEEP_MIN_POINTS", "0")
+    monkeypatch.setenv("INTERPN_B200_SWEEP_MIN_ROWS", "0")
+    monkeypatch.setenv("INTERPN_B200_SWEEP_SLAB_KB", "0")
+    monkeypatch.setenv("INTERPN_B200_SWEEP_CHUNK", "150000")
+    if ndims % 2 == 0:
+        monkeypatch.setenv("INTERPN_B200_WINDOW_MIN_KB", "0")  # sweep over the window layouts as well
+    rng = np.random.default_rng(77 * ndims + len(method))
+    min_dim = {2: 8, 3: 5}.get(ndims, 4 if method == "cubic" else 2)
+    max_dim = {2: 40, 3: 14, 4: 9, 6: 5, 8: 4}[ndims]
+    n = 700_001 if ndims <= 4 else 50_001
+    dims, grids, starts, steps, vals, obs = random_case(rng, ndims, n, min_dim, max(max_dim, min_dim), dtype)
+    sfx = "f64" if dtype == np.float64 else "f32"
+    before = ib.swept_launch_count()
+    lin = bool(ndims % 2)
+    extra = (lin,) if method == "cubic" else ()
+    out = np.zeros(n, dtype=dtype)
+    getattr(ib.raw, f"interpn_{method}_regular_{sfx}")(dims, starts, steps, vals, *extra, obs, out)
+    assert_same_bits(out, oracle.interpn_regular(method, dims, starts, steps, vals, obs, linearize_extrapolation=lin, nthreads=8))
+    out = np.zeros(n, dtype=dtype)
+    getattr(ib.raw, f"interpn_{method}_rectilinear_{sfx}")(grids, vals, *extra, obs, out)
+    assert_same_bits(out, oracle.interpn_rectilinear(method, grids, vals, obs, linearize_extrapolation=lin, nthreads=8))
+    assert ib.swept_launch_count() >= before + 2, "the bin-swept kernels did not run"
+    # reference failure semantics survive the reordering: the smallest failing index is reported and
+    # everything before it is written
+    bad = [n // 3, n // 3 + 5000]
+    obs2 = [o.copy() for o in obs]
+    for b in bad:
+        obs2[0][b] = np.nan
+    out = np.full(n, -7.0, dtype=dtype)
+    with pytest.raises(AssertionError, match="Unrepresentable coordinate value"):
+        getattr(ib.raw, f"interpn_{method}_regular_{sfx}")(dims, starts, steps, vals, *extra, obs2, out)
+    want = oracle.interpn_regular(method, dims, starts, steps, vals, [o[: bad[0]] for o in obs], linearize_extrapolation=lin, nthreads=8)
+    assert_same_bits(out[: bad[0]], want)
+    assert np.all(out[bad[0] :] == -7.0)
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])

@@ -276,7 +276,7 @@ int window_width(const DeviceGrid& g) {
     size_t max_mb = 8192;
     if (const char* e = getenv("INTERPN_B200_WINDOW_MB")) max_mb = static_cast<size_t>(strtoull(e, nullptr, 10));
     const size_t bytes = g.nvals * static_cast<size_t>(g.elem);
-    size_t min_kb = 128;  // smaller grids live in L1 anyway
+    size_t min_kb = 0;  // even L1-resident grids gain: half (linear) or a quarter (cubic) as many load instructions
     if (const char* e = getenv("INTERPN_B200_WINDOW_MIN_KB")) min_kb = static_cast<size_t>(strtoull(e, nullptr, 10));
     if (bytes < (min_kb << 10) || bytes * w > (max_mb << 20)) return 0;
     if (bytes * w > (size_t(64) << 20)) {
@@ -392,6 +392,57 @@ int rect_new(int method, const T* const* grids, const size_t* grid_lens, size_t 
         g.dim[d] = static_cast<int>(grid_lens[d]);
         g.axis_off[d] = static_cast<int>(packed.size());
         packed.insert(packed.end(), grids[d], grids[d] + grid_lens[d]);
+    }
+    // Search accelerators (kernels.cuh rect_lower_bound), valid only for strictly increasing finite axes — the
+    // reference itself checks just the first two nodes (multilinear/rectilinear.rs:194-198), and on anything else
+    // the kernels keep the plain bisection. Per axis: reciprocal cell widths (f64: exact_div's divisor table) and
+    // a bucket table lut[k] = partition_point(g < g0 + k*(g_last-g0)/nb), stored as ints in the same blob.
+    bool sorted = true, widths_ok = sizeof(T) == 8;
+    for (size_t d = 0; d < ngrids && sorted; ++d) {
+        for (size_t i = 0; i < grid_lens[d]; ++i) {
+            const double v = static_cast<double>(grids[d][i]);
+            if (!(v - v == 0.0)) sorted = false;  // NaN / inf
+            if (i && !(grids[d][i] > grids[d][i - 1])) sorted = false;
+            if (i) {
+                const double w = static_cast<double>(grids[d][i]) - static_cast<double>(grids[d][i - 1]);
+                if (!(w >= 0x1p-300 && w < 0x1p301)) widths_ok = false;
+            }
+        }
+    }
+    g.rect_fast = sorted ? 1 : 0;
+    g.rect_fast_div = sorted && widths_ok ? 1 : 0;
+    if (sorted) {
+        for (size_t d = 0; d < ngrids; ++d) {
+            const size_t n = grid_lens[d];
+            g.rc_off[d] = static_cast<int>(packed.size());
+            for (size_t i = 0; i + 1 < n; ++i) {
+                volatile T w = grids[d][i + 1] - grids[d][i];  // the kernels' divisor, rounded in T
+                packed.push_back(static_cast<T>(T(1) / w));
+            }
+            size_t nb = 2 * n;
+            if (nb > 65536) nb = 65536;
+            std::vector<int> lut(nb + 1);
+            const double g0 = static_cast<double>(grids[d][0]), span = static_cast<double>(grids[d][n - 1]) - g0;
+            lut[0] = 0;
+            lut[nb] = static_cast<int>(n);
+            for (size_t k = 1; k < nb; ++k) {
+                const double edge = g0 + span * (static_cast<double>(k) / static_cast<double>(nb));
+                size_t lo = 0, hi = n;
+                while (lo < hi) {
+                    const size_t mid = (lo + hi) / 2;
+                    if (static_cast<double>(grids[d][mid]) < edge) lo = mid + 1;
+                    else hi = mid;
+                }
+                lut[k] = static_cast<int>(lo);
+            }
+            g.lut_off[d] = static_cast<int>(packed.size());
+            g.lut_nb[d] = static_cast<int>(nb);
+            g.lut_scale[d] = static_cast<double>(nb) / span;
+            const size_t slots = ((nb + 1) * sizeof(int) + sizeof(T) - 1) / sizeof(T);
+            const size_t at = packed.size();
+            packed.resize(at + slots, T(0));
+            memcpy(packed.data() + at, lut.data(), (nb + 1) * sizeof(int));
+        }
     }
     g.axes_total = static_cast<int>(packed.size());
     set_strides(g);

@@ -29,7 +29,13 @@ struct DeviceGrid {
     int win_cross = 0;         // cubic, N = 2..4: the cross-window layout of kernels.cuh cubic_quad_point
     void* axes = nullptr;           // device, all rectilinear axes packed back to back
     int axis_off[kMaxNd] = {};      // element offset of axis d inside `axes`
-    int axes_total = 0;
+    int axes_total = 0;             // elements of the whole blob: axes, then reciprocal cell widths, then bucket tables
+    int rect_fast = 0;              // axes strictly increasing and finite: bucket-table search is valid
+    int rect_fast_div = 0;          // ... and (f64) every cell width within exact_div's range
+    int rc_off[kMaxNd] = {};        // element offset of axis d's reciprocal cell widths (dim-1 entries)
+    int lut_off[kMaxNd] = {};       // element offset of axis d's bucket table (lut_nb+1 ints)
+    int lut_nb[kMaxNd] = {};
+    double lut_scale[kMaxNd] = {};  // buckets per unit length
     int sm_count = 148;
 };
 

@@ -29,7 +29,10 @@ struct EvalArgs {
     double hstep[N], tau[N], lim[N];  // regular f64: step/2, step*2^-54, step*(1-2^-20) (device_math.cuh fast_cell)
     const T* axes;    // rectilinear: packed axes (global)
     int axis_off[N];  // rectilinear
-    int axes_total;   // rectilinear
+    int axes_total;   // rectilinear: elements of the blob (axes, reciprocal cell widths, bucket tables)
+    int rect_fast, rect_fast_div;  // rectilinear: search / division accelerators are valid (capi.cu rect_new)
+    int rc_off[N], lut_off[N], lut_nb[N];
+    T lut_scale[N];
     int axes_in_smem;
     int linearize;
     unsigned long long* first_bad;
@@ -57,6 +60,29 @@ __device__ __forceinline__ const T* stage_axes(const EvalArgs<T, N>& a) {
     for (int i = threadIdx.x; i < a.axes_total; i += blockDim.x) s[i] = a.axes[i];
     __syncthreads();
     return s;
+}
+
+// partition_point(|g| g < x) on axis d. On strictly increasing axes a bucket table narrows the bisection to
+// the nodes of three adjacent buckets (two buckets per node on average): the computed bucket is within one of
+// the true one, lut[k] = partition_point(g < edge_k) is monotone in k, so the answer lies in
+// [lut[b-1], lut[b+2]] and any correct search inside that range returns the reference's index. NaN compares
+// false everywhere -> 0, +-inf saturate to the end buckets, like slice::partition_point.
+template <class T, int N>
+__device__ __forceinline__ int rect_lower_bound(const EvalArgs<T, N>& a, const T* __restrict__ axes, int d, T x) {
+    const T* g = axes + a.axis_off[d];
+    if (!a.rect_fast) return lower_bound(g, a.dim[d], x);
+    const int* lut = reinterpret_cast<const int*>(axes + a.lut_off[d]);
+    const int nb = a.lut_nb[d];
+    const int b = min(max(Ops<T>::floor_sat((x - g[0]) * a.lut_scale[d]), 0), nb - 1);
+    int lo = lut[max(b - 1, 0)];
+    int len = lut[min(b + 2, nb)] - lo;
+    while (len > 0) {
+        const int half = len >> 1;
+        const bool below = g[lo + half] < x;
+        lo = below ? lo + half + 1 : lo;
+        len = below ? len - half - 1 : half;
+    }
+    return lo;
 }
 
 // Records an unrepresentable query point: the smallest failing index of the caller's batch wins.
@@ -195,10 +221,16 @@ __device__ __forceinline__ bool linear_locate(const EvalArgs<T, N>& a, const T* 
         int origin;
         if constexpr (RECT) {
             const T* g = axes + a.axis_off[d];
-            origin = clamp_cell(lower_bound(g, a.dim[d], x) - 1, a.dim[d] - 2);
-            T x0 = g[origin];
-            T x1 = g[origin + 1];
-            t[d] = O::div(O::sub(x, x0), O::sub(x1, x0));
+            origin = clamp_cell(rect_lower_bound<T, N>(a, axes, d, x) - 1, a.dim[d] - 2);
+            const T x0 = g[origin];
+            const T x1 = g[origin + 1];
+            const T e = O::sub(x, x0), h = O::sub(x1, x0);
+            if constexpr (sizeof(T) == 8) {
+                // the cell's reciprocal width is tabulated: exact_div instead of the IEEE division
+                t[d] = a.rect_fast_div ? exact_div(e, h, axes[a.rc_off[d] + origin], true) : O::div(e, h);
+            } else {
+                t[d] = O::div(e, h);
+            }
         } else {
             int iloc = 0;
             ok = floor_cell(x, a.start[d], a.step[d], a.rstep[d], a.fast_div != 0, iloc) && ok;
@@ -227,10 +259,17 @@ __device__ __forceinline__ bool nearest_locate(const EvalArgs<T, N>& a, const T*
         T dt;
         if constexpr (RECT) {
             const T* g = axes + a.axis_off[d];
-            origin = clamp_cell(lower_bound(g, a.dim[d], x) - 1, a.dim[d] - 2);
-            T x0 = g[origin];
-            T x1 = g[origin + 1];
-            dt = O::div(O::sub(x, x0), O::sub(x1, x0));
+            origin = clamp_cell(rect_lower_bound<T, N>(a, axes, d, x) - 1, a.dim[d] - 2);
+            const T x0 = g[origin];
+            const T x1 = g[origin + 1];
+            const T e = O::sub(x, x0), h = O::sub(x1, x0);
+            if constexpr (sizeof(T) == 8) {
+                if (a.rect_fast_div) {  // division-free and exact: device_math.cuh nearest_upper
+                    idx += static_cast<I>(origin + (nearest_upper(e, h * 0.5, h * 0x1p-54) ? 1 : 0)) * stride[d];
+                    continue;
+                }
+            }
+            dt = O::div(e, h);
         } else {
             int iloc = 0;
             ok = floor_cell(x, a.start[d], a.step[d], a.rstep[d], a.fast_div != 0, iloc) && ok;
@@ -511,12 +550,12 @@ struct CubicRectDim {
 };
 
 template <class T>
-__device__ __forceinline__ void cubic_rect_locate(T x, const T* __restrict__ g, int dim, int linearize, int& origin,
-                                                  CubicRectDim<T>& c) {
+__device__ __forceinline__ void cubic_rect_locate(T x, const T* __restrict__ g, int pp, int dim, int linearize, int& origin,
+                                                  CubicRectDim<T>& c) {  // pp = partition_point(g < x)
     using O = Ops<T>;
     const T one = T(1);
     const int n = dim;
-    const int iloc = lower_bound(g, dim, x) - 2;
+    const int iloc = pp - 2;
     origin = clamp_cell(iloc, dim - 4);
     bool outside;
     if (iloc == -2) { c.mode = kModeLow; outside = true; }
@@ -670,7 +709,7 @@ __device__ __forceinline__ bool cubic_point(const EvalArgs<T, N>& a, const T* __
         const T x = xs[d];
         int origin;
         if constexpr (RECT) {
-            cubic_rect_locate(x, axes + a.axis_off[d], a.dim[d], a.linearize, origin, c[d]);
+            cubic_rect_locate(x, axes + a.axis_off[d], rect_lower_bound<T, N>(a, axes, d, x), a.dim[d], a.linearize, origin, c[d]);
         } else {
             ok = cubic_regular_locate(x, a.start[d], a.step[d], a.rstep[d], a.fast_div != 0, a.dim[d], a.linearize, origin,
                                       c[d]) && ok;
@@ -746,7 +785,7 @@ __device__ __forceinline__ bool cubic_quad_point(const EvalArgs<T, N>& a, const 
     int origin;
     bool ok = true;
     if constexpr (RECT) {
-        cubic_rect_locate(x, axes + a.axis_off[dmine], a.dim[dmine], a.linearize, origin, mine);
+        cubic_rect_locate(x, axes + a.axis_off[dmine], rect_lower_bound<T, N>(a, axes, dmine, x), a.dim[dmine], a.linearize, origin, mine);
     } else {
         ok = cubic_regular_locate(x, a.start[dmine], a.step[dmine], a.rstep[dmine], a.fast_div != 0, a.dim[dmine],
                                   a.linearize, origin, mine);

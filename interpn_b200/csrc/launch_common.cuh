@@ -25,6 +25,10 @@ inline EvalArgs<T, N> make_args(const DeviceGrid& g, const T* const* obs, size_t
         a.step[d] = static_cast<T>(g.step[d]);
         a.rstep[d] = T(1) / a.step[d];  // correctly rounded in T (host IEEE division)
         a.axis_off[d] = g.axis_off[d];
+        a.rc_off[d] = g.rc_off[d];
+        a.lut_off[d] = g.lut_off[d];
+        a.lut_nb[d] = g.lut_nb[d];
+        a.lut_scale[d] = static_cast<T>(g.lut_scale[d]);
     }
     a.out = out;
     a.n = n;
@@ -44,6 +48,8 @@ inline EvalArgs<T, N> make_args(const DeviceGrid& g, const T* const* obs, size_t
     }
     a.axes = static_cast<const T*>(g.axes);
     a.axes_total = g.axes_total;
+    a.rect_fast = g.rect_fast;
+    a.rect_fast_div = g.rect_fast_div;
     a.axes_in_smem = g.rect && static_cast<size_t>(g.axes_total) * sizeof(T) <= kAxesSmemBudget;
     a.linearize = g.linearize;
     a.first_bad = first_bad;
@@ -82,22 +88,36 @@ constexpr int linear_points_per_thread() {
     return N <= 3 ? IB200_P_LINEAR_LO : (N <= 5 ? IB200_P_LINEAR_HI : 1);
 }
 
+struct LaunchOpts {
+    int points_per_thread = 1;
+    const unsigned* remap = nullptr;     // bin-swept path: original indices of the sorted points
+    unsigned long long* work = nullptr;  // bin-swept path: dynamic block scheduling counter
+    int threads_per_point = 1;           // 4 for the quad-cooperative kernels
+    bool window = false;                 // the kernel gathers from the window copy, not from vals
+    int ctas_per_sm = 8;
+};
+
 template <class T, int N, class K>
 inline cudaError_t launch_generic(K kernel, const DeviceGrid& g, const T* const* obs, size_t n, T* out,
                                   unsigned long long* first_bad, unsigned long long index_base, cudaStream_t stream,
-                                  int points_per_thread = 1, const unsigned* remap = nullptr,
-                                  unsigned long long* work = nullptr, int threads_per_point = 1, int ctas_per_sm = 8) {
+                                  const LaunchOpts& o = LaunchOpts()) {
     if (n == 0) return cudaSuccess;
-    EvalArgs<T, N> a = make_args<T, N>(g, obs, n, out, first_bad, index_base, remap, work);
+    const int points_per_thread = o.points_per_thread, threads_per_point = o.threads_per_point, ctas_per_sm = o.ctas_per_sm;
+    EvalArgs<T, N> a = make_args<T, N>(g, obs, n, out, first_bad, index_base, o.remap, o.work);
     size_t smem = a.axes_in_smem ? static_cast<size_t>(g.axes_total) * sizeof(T) : 0;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
     }
     const size_t items = (n + points_per_thread - 1) / points_per_thread * threads_per_point;
-    kernel<<<grid_for(items, g.sm_count, ctas_per_sm), kBlock, smem, stream>>>(a);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid_for(items, g.sm_count, ctas_per_sm));
+    cfg.blockDim = dim3(kBlock);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kernel, a);
     count_launch();
-    return cudaGetLastError();
+    return le != cudaSuccess ? le : cudaGetLastError();
 }
 
 // Window-layout kernels are instantiated up to these dimensionalities (interp_internal.h mirrors them

@@ -13,17 +13,25 @@ cudaError_t launch_cubic_rect(const DeviceGrid& g, const T* const* obs, size_t n
     auto direct = [&](bool win, const T* const* o, size_t cnt, T* dst, unsigned long long base, const unsigned* remap,
                       unsigned long long* work) {
         cudaError_t e = cudaErrorInvalidValue;
+        auto lo = [&](int threads_per_point, bool window) {
+            LaunchOpts r;
+            r.remap = remap;
+            r.work = work;
+            r.threads_per_point = threads_per_point;
+            r.window = window;
+            return r;
+        };
         if (win && g.ndims == 1) {
-            e = launch_generic<T, 1>(cubic_kernel<T, 1, true, true, 1>, g, o, cnt, dst, first_bad, base, stream, 1, remap, work);
+            e = launch_generic<T, 1>(cubic_kernel<T, 1, true, true, 1>, g, o, cnt, dst, first_bad, base, stream, lo(1, true));
         } else if (win) {
             switch (g.ndims) {
-                case 2: e = launch_generic<T, 2>(cubic_quad_kernel<T, 2, true, IB200_MINB_QUAD2>, g, o, cnt, dst, first_bad, base, stream, 1, remap, work, 4); break;
-                case 3: e = launch_generic<T, 3>(cubic_quad_kernel<T, 3, true, IB200_MINB_QUAD3_RECT>, g, o, cnt, dst, first_bad, base, stream, 1, remap, work, 4); break;
-                case 4: e = launch_generic<T, 4>(cubic_quad_kernel<T, 4, true, IB200_MINB_QUAD4>, g, o, cnt, dst, first_bad, base, stream, 1, remap, work, 4); break;
+                case 2: e = launch_generic<T, 2>(cubic_quad_kernel<T, 2, true, IB200_MINB_QUAD2>, g, o, cnt, dst, first_bad, base, stream, lo(4, true)); break;
+                case 3: e = launch_generic<T, 3>(cubic_quad_kernel<T, 3, true, IB200_MINB_QUAD3_RECT>, g, o, cnt, dst, first_bad, base, stream, lo(4, true)); break;
+                case 4: e = launch_generic<T, 4>(cubic_quad_kernel<T, 4, true, IB200_MINB_QUAD4>, g, o, cnt, dst, first_bad, base, stream, lo(4, true)); break;
                 default: break;
             }
         } else {
-            IB200_SWITCH_N(8, e = (launch_generic<T, N>(cubic_kernel<T, N, true, false, cubic_min_blocks<N, true>()>, g, o, cnt, dst, first_bad, base, stream, 1, remap, work));)
+            IB200_SWITCH_N(8, e = (launch_generic<T, N>(cubic_kernel<T, N, true, false, cubic_min_blocks<N, true>()>, g, o, cnt, dst, first_bad, base, stream, lo(1, false)));)
         }
         return e;
     };

@@ -9,11 +9,19 @@ cudaError_t launch_linear_direct(const DeviceGrid& g, const T* const* obs, size_
                                  unsigned long long index_base, cudaStream_t stream, const unsigned* remap,
                                  unsigned long long* work) {
     constexpr int P = linear_points_per_thread<N>();
+    auto opts = [&](int ppt) {
+        LaunchOpts o;
+        o.points_per_thread = ppt;
+        o.remap = remap;
+        o.work = work;
+        o.window = WIN;
+        return o;
+    };
     if (g.nvals >= (size_t(1) << 31))  // 64-bit index arithmetic: the basic kernel only
-        return launch_generic<T, N>(linear_kernel<T, N, RECT, false, 1, long long>, g, obs, n, out, first_bad, index_base, stream, 1, remap, work);
+        return launch_generic<T, N>(linear_kernel<T, N, RECT, false, 1, long long>, g, obs, n, out, first_bad, index_base, stream, opts(1));
     if (P > 1 && n >= static_cast<size_t>(P) && vector_aligned<T>(obs, N, out, P))
-        return launch_generic<T, N>(linear_kernel<T, N, RECT, WIN, P, int>, g, obs, n, out, first_bad, index_base, stream, P, remap, work);
-    return launch_generic<T, N>(linear_kernel<T, N, RECT, WIN, 1, int>, g, obs, n, out, first_bad, index_base, stream, 1, remap, work);
+        return launch_generic<T, N>(linear_kernel<T, N, RECT, WIN, P, int>, g, obs, n, out, first_bad, index_base, stream, opts(P));
+    return launch_generic<T, N>(linear_kernel<T, N, RECT, WIN, 1, int>, g, obs, n, out, first_bad, index_base, stream, opts(1));
 }
 
 template <class T, int N, bool RECT>

@@ -8,6 +8,8 @@ cudaError_t launch_nearest(const DeviceGrid& g, const T* const* obs, size_t n, T
                            unsigned long long index_base, cudaStream_t stream) {
     cudaError_t err = cudaErrorInvalidValue;
     constexpr int P = IB200_P_NEAREST;
+    LaunchOpts popts;
+    popts.points_per_thread = P;
     const bool vec = P > 1 && n >= static_cast<size_t>(P) && vector_aligned<T>(obs, g.ndims, out, P);
     if (g.nvals >= (size_t(1) << 31)) {  // 64-bit index arithmetic: the basic kernel only
         if (g.rect) {
@@ -19,13 +21,13 @@ cudaError_t launch_nearest(const DeviceGrid& g, const T* const* obs, size_t n, T
     }
     if (g.rect) {
         if (vec) {
-            IB200_SWITCH_N(6, err = (launch_generic<T, N>(nearest_kernel<T, N, true, P, int>, g, obs, n, out, first_bad, index_base, stream, P));)
+            IB200_SWITCH_N(6, err = (launch_generic<T, N>(nearest_kernel<T, N, true, P, int>, g, obs, n, out, first_bad, index_base, stream, popts));)
         } else {
             IB200_SWITCH_N(6, err = (launch_generic<T, N>(nearest_kernel<T, N, true, 1, int>, g, obs, n, out, first_bad, index_base, stream));)
         }
     } else {
         if (vec) {
-            IB200_SWITCH_N(6, err = (launch_generic<T, N>(nearest_kernel<T, N, false, P, int>, g, obs, n, out, first_bad, index_base, stream, P));)
+            IB200_SWITCH_N(6, err = (launch_generic<T, N>(nearest_kernel<T, N, false, P, int>, g, obs, n, out, first_bad, index_base, stream, popts));)
         } else {
             IB200_SWITCH_N(6, err = (launch_generic<T, N>(nearest_kernel<T, N, false, 1, int>, g, obs, n, out, first_bad, index_base, stream));)
         }

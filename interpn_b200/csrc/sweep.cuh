@@ -41,7 +41,7 @@ struct SweepKey {
 template <class T, int N, bool RECT>
 __device__ __forceinline__ int sweep_cell(const EvalArgs<T, N>& a, const T* __restrict__ axes, int d, T x) {
     if constexpr (RECT) {
-        return clamp_cell(lower_bound(axes + a.axis_off[d], a.dim[d], x) - 1, a.dim[d] - 2);
+        return clamp_cell(rect_lower_bound<T, N>(a, axes, d, x) - 1, a.dim[d] - 2);
     } else {
         return clamp_cell(Ops<T>::floor_sat((x - a.start[d]) * a.rstep[d]), a.dim[d] - 2);
     }

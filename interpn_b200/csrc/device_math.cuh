@@ -28,6 +28,8 @@ struct Ops<double> {
     static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
     static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
     static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+    // Only where the fused result provably equals the two-operation sequence (exact inner product).
+    static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
     static __device__ __forceinline__ double floor(double a) { return ::floor(a); }
     static __device__ __forceinline__ double abs(double a) { return ::fabs(a); }
     static __device__ __forceinline__ double from_int(int i) { return __int2double_rn(i); }
@@ -41,6 +43,7 @@ struct Ops<float> {
     static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
     static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
     static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+    static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
     static __device__ __forceinline__ float floor(float a) { return ::floorf(a); }
     static __device__ __forceinline__ float abs(float a) { return ::fabsf(a); }
     static __device__ __forceinline__ float from_int(int i) { return __int2float_rn(i); }

@@ -1,5 +1,6 @@
 // launch_cubic_regular.cu — multicubic regular-grid launchers (f32/f64, N = 1..8).
 #include "sweep.cuh"
+#include "cubic_quad4.cuh"
 
 namespace ib200 {
 
@@ -24,11 +25,31 @@ cudaError_t launch_cubic_regular(const DeviceGrid& g, const T* const* obs, size_
         if (win && g.ndims == 1) {
             e = launch_generic<T, 1>(cubic_kernel<T, 1, false, true, 1>, g, o, cnt, dst, first_bad, base, stream, lo(1, true));
         } else if (win) {
-            switch (g.ndims) {
-                case 2: e = launch_generic<T, 2>(cubic_quad_kernel<T, 2, false, IB200_MINB_QUAD2>, g, o, cnt, dst, first_bad, base, stream, lo(4, true)); break;
-                case 3: e = launch_generic<T, 3>(cubic_quad_kernel<T, 3, false, IB200_MINB_QUAD3>, g, o, cnt, dst, first_bad, base, stream, lo(4, true)); break;
-                case 4: e = launch_generic<T, 4>(cubic_quad_kernel<T, 4, false, IB200_MINB_QUAD4>, g, o, cnt, dst, first_bad, base, stream, lo(4, true)); break;
-                default: break;
+            // Four points per quad (cubic_quad4.cuh); INTERPN_B200_CUBIC_QUAD=1 selects the one-point-per-quad
+            // kernel of kernels.cuh, INTERPN_B200_QUAD4_MINB the register budget (CTAs per SM) for tuning runs.
+            static const int variant = static_cast<int>(sweep_env("INTERPN_B200_CUBIC_QUAD", 4));
+            static const int minb = static_cast<int>(sweep_env("INTERPN_B200_QUAD4_MINB", 0));
+            if (variant == 4) {
+                switch (g.ndims) {
+                    case 2: e = launch_generic<T, 2>(cubic_quad4_kernel<T, 2, 4>, g, o, cnt, dst, first_bad, base, stream, lo(1, true)); break;
+                    case 3:
+                        if (minb == 2) e = launch_generic<T, 3>(cubic_quad4_kernel<T, 3, 2>, g, o, cnt, dst, first_bad, base, stream, lo(1, true));
+                        else if (minb == 3) e = launch_generic<T, 3>(cubic_quad4_kernel<T, 3, 3>, g, o, cnt, dst, first_bad, base, stream, lo(1, true));
+                        else e = launch_generic<T, 3>(cubic_quad4_kernel<T, 3, 4>, g, o, cnt, dst, first_bad, base, stream, lo(1, true));
+                        break;
+                    case 4:
+                        if (minb == 3) e = launch_generic<T, 4>(cubic_quad4_kernel<T, 4, 3>, g, o, cnt, dst, first_bad, base, stream, lo(1, true));
+                        else e = launch_generic<T, 4>(cubic_quad4_kernel<T, 4, 2>, g, o, cnt, dst, first_bad, base, stream, lo(1, true));
+                        break;
+                    default: break;
+                }
+            } else {
+                switch (g.ndims) {
+                    case 2: e = launch_generic<T, 2>(cubic_quad_kernel<T, 2, false, IB200_MINB_QUAD2>, g, o, cnt, dst, first_bad, base, stream, lo(4, true)); break;
+                    case 3: e = launch_generic<T, 3>(cubic_quad_kernel<T, 3, false, IB200_MINB_QUAD3>, g, o, cnt, dst, first_bad, base, stream, lo(4, true)); break;
+                    case 4: e = launch_generic<T, 4>(cubic_quad_kernel<T, 4, false, IB200_MINB_QUAD4>, g, o, cnt, dst, first_bad, base, stream, lo(4, true)); break;
+                    default: break;
+                }
             }
         } else {
             IB200_SWITCH_N(8, e = (launch_generic<T, N>(cubic_kernel<T, N, false, false, cubic_min_blocks<N, false>()>, g, o, cnt, dst, first_bad, base, stream, lo(1, false)));)

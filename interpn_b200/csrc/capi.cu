@@ -8,6 +8,7 @@
 
 #include <atomic>
 #include <climits>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -362,6 +363,66 @@ int regular_new(int method, const size_t* dims, size_t ndims, const T* starts, s
     return INTERPN_B200_OK;
 }
 
+// Per-cell constants of the 1-D cubic step on a rectilinear axis (cubic_quad4.cuh). Everything the reference's
+// interp_inner (multicubic/rectilinear.rs:413-545) derives from the four axis nodes of a footprint depends only on
+// pp = partition_point(g < x) in 0..=n: the footprint origin clamp(pp-2, 0, n-4), the saturation class, the spacing
+// ratios and the centered_difference_nonuniform weights (multicubic/mod.rs:103-117). They are computed here once,
+// in T, with the same IEEE operations in the same order as kernels.cuh cubic_rect_locate (this file is compiled with
+// -ffp-contract=off), so a kernel that reads them gets the bits it would have computed — without eight divisions per
+// dimension per query point. Only built for strictly increasing finite axes (no NaN/inf can arise).
+// Row layout (12 elements): wa, wc (exchanged in a low end cell, see cubic_quad4.cuh), div0, 1/div0, wa1, wc1, div1,
+// 1/div1, gref, href, 1/href (t = +-(x - gref)/href), flags (int bits: CubicMode | outside<<2 | ratios in exact_div's
+// range<<3 | href in range<<4).
+template <class T>
+void cubic_cell_table(const T* g, size_t n, std::vector<T>& packed) {
+    auto in_range = [](T v) {
+        const double a = std::fabs(static_cast<double>(v));
+        return sizeof(T) == 8 && a >= 0x1p-300 && a < 0x1p301;
+    };
+    const T one = T(1);
+    for (size_t pp = 0; pp <= n; ++pp) {
+        const long iloc = static_cast<long>(pp) - 2;
+        const long nn = static_cast<long>(n);
+        const long origin = iloc < 0 ? 0 : (iloc > nn - 4 ? nn - 4 : iloc);
+        int mode, outside;
+        if (iloc == -2) { mode = 1; outside = 1; }
+        else if (iloc == -1) { mode = 1; outside = 0; }
+        else if (iloc == nn - 2) { mode = 2; outside = 1; }
+        else if (iloc == nn - 3) { mode = 2; outside = 0; }
+        else { mode = 0; outside = 0; }
+        volatile T g0 = g[origin], g1 = g[origin + 1], g2 = g[origin + 2], g3 = g[origin + 3];
+        volatile T h01 = g1 - g0, h12 = g2 - g1, h23 = g3 - g2;
+        volatile T wa, wc, div0, wa1 = one, wc1 = one, div1 = one, gref, href;
+        if (mode == 0) {
+            volatile T r = h01 / h12;
+            volatile T rp = r + one, pr = one + r;
+            wa = r / rp; wc = one / pr; div0 = r;
+            volatile T s = h23 / h12;
+            volatile T ps = one + s, sp = s + one;
+            wa1 = one / ps; wc1 = s / sp; div1 = s;
+            gref = g1; href = h12;
+        } else if (mode == 1) {
+            volatile T q = h12 / h01;
+            volatile T pq = one + q, qp = q + one;
+            volatile T a = one / pq, c = q / qp;
+            wa = c; wc = a;  // exchanged: see the header comment
+            div0 = q;
+            gref = g1; href = h01;
+        } else {
+            volatile T p = h12 / h23;
+            volatile T pp1 = p + one, p1p = one + p;
+            wa = p / pp1; wc = one / p1p; div0 = p;
+            gref = g2; href = h23;
+        }
+        volatile T rdiv0 = one / div0, rdiv1 = one / div1, rhref = one / href;
+        const int flags = mode | (outside << 2) | ((in_range(div0) && in_range(div1)) ? 8 : 0) | (in_range(href) ? 16 : 0);
+        T fbits = T(0);
+        memcpy(&fbits, &flags, sizeof(int));
+        const T row[12] = {wa, wc, div0, rdiv0, wa1, wc1, div1, rdiv1, gref, href, rhref, fbits};
+        packed.insert(packed.end(), row, row + 12);
+    }
+}
+
 template <class T>
 int rect_new(int method, const T* const* grids, const size_t* grid_lens, size_t ngrids, const T* vals, size_t nvals,
              int linearize, int vals_location, interpn_b200_interp** out) {
@@ -443,6 +504,14 @@ int rect_new(int method, const T* const* grids, const size_t* grid_lens, size_t 
             packed.resize(at + slots, T(0));
             memcpy(packed.data() + at, lut.data(), (nb + 1) * sizeof(int));
         }
+    }
+    if (sorted && method == INTERPN_B200_CUBIC) {
+        for (size_t d = 0; d < ngrids; ++d) {
+            while (packed.size() * sizeof(T) % 16) packed.push_back(T(0));  // rows are read as 16-byte vectors
+            g.ct_off[d] = static_cast<int>(packed.size());
+            cubic_cell_table<T>(grids[d], grid_lens[d], packed);
+        }
+        g.rect_cubic_table = 1;
     }
     g.axes_total = static_cast<int>(packed.size());
     set_strides(g);

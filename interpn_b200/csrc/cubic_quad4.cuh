@@ -24,28 +24,84 @@
 
 namespace ib200 {
 
-template <class T, int N>
-struct alignas(16) QuadSlot {
-    T tt[N];    // per dimension: t (interior), -t (low end), t - 1 (high end)
-    int base;   // flat index of the footprint's first corner
-    int flags;  // per dimension d: bits 3d..3d+1 = CubicMode, bit 3d+2 = linearized extrapolation applies
+// Per-dimension parameters of a 1-D step.
+template <class T, bool RECT>
+struct QuadDim {
+    T tt;  // t (interior), -t (low end), t - 1 (high end)
 };
+// Rectilinear grids: the spacing ratios and centered_difference_nonuniform weights of the active formula, with wa/wc
+// exchanged in a low end cell so that one expression serves all classes. They depend on the cell only and come from
+// the per-axis table built at construction (capi.cu cubic_cell_table), staged in shared memory with the axes.
+template <class T>
+struct QuadDim<T, true> {
+    T tt, wa, wc, div0, rdiv0, wa1, wc1, div1, rdiv1;
+};
+constexpr int kCubicCellRow = 12;  // elements per table row (capi.cu cubic_cell_table)
+
+// What the owner of a point publishes to its quad. flags, four bits per dimension d: bits 4d..4d+1 = CubicMode,
+// bit 4d+2 = linearized extrapolation applies, bit 4d+3 = the spacing ratios are within exact_div's range (rectilinear).
+template <class T, int N, bool RECT>
+struct alignas(16) QuadSlot {
+    T tt[N];
+    int base;  // flat index of the footprint's first corner
+    int flags;
+};
+template <class T, int N>
+struct alignas(16) QuadSlot<T, N, true> {
+    T tt[N];
+    int pp[N];  // partition_point(g < x) per dimension = row of the cell table
+    int base;
+    int flags;
+};
+
+template <class T, int N>
+__device__ __forceinline__ QuadDim<T, false> quad4_dim(const EvalArgs<T, N>&, const T*, const QuadSlot<T, N, false>* sp, int d) {
+    return QuadDim<T, false>{sp->tt[d]};
+}
+template <class T, int N>
+__device__ __forceinline__ QuadDim<T, true> quad4_dim(const EvalArgs<T, N>& a, const T* __restrict__ axes,
+                                                      const QuadSlot<T, N, true>* sp, int d) {
+    const T* row = axes + a.ct_off[d] + sp->pp[d] * kCubicCellRow;
+    QuadDim<T, true> c;
+    c.tt = sp->tt[d];
+    if constexpr (sizeof(T) == 8) {
+        const double2 r0 = reinterpret_cast<const double2*>(row)[0], r1 = reinterpret_cast<const double2*>(row)[1];
+        const double2 r2 = reinterpret_cast<const double2*>(row)[2], r3 = reinterpret_cast<const double2*>(row)[3];
+        c.wa = r0.x; c.wc = r0.y; c.div0 = r1.x; c.rdiv0 = r1.y; c.wa1 = r2.x; c.wc1 = r2.y; c.div1 = r3.x; c.rdiv1 = r3.y;
+    } else {
+        const float4 r0 = reinterpret_cast<const float4*>(row)[0], r1 = reinterpret_cast<const float4*>(row)[1];
+        c.wa = r0.x; c.wc = r0.y; c.div0 = r0.z; c.rdiv0 = r0.w; c.wa1 = r1.x; c.wc1 = r1.y; c.div1 = r1.z; c.rdiv1 = r1.w;
+    }
+    return c;
+}
+
+template <class T>
+__device__ __forceinline__ T hermite_fused(T t, T y0, T dy, T k0, T k1) {  // device_math.cuh hermite with c2 fused
+    using O = Ops<T>;
+    const T a = O::sub(k0, dy);
+    const T b = O::sub(dy, k1);
+    const T c1 = O::add(dy, a);
+    const T c2 = O::fma(T(-2), a, b);
+    const T c3 = O::sub(a, b);
+    return O::add(y0, O::mul(t, O::add(c1, O::mul(t, O::add(c2, O::mul(t, c3))))));
+}
 
 // One 1-D cubic step on inputs that are already permuted for the saturation class:
 //   interior (v0,v1,v2,v3)   low end (v2,v1,v0,*)   high end (v1,v2,v3,*)
-// `edge` = this lane is in an end cell (k1 is the natural-spline slope), `lin` = outside the grid with
-// linearize_extrapolation; `all_none` is warp-uniform (no lane of the warp has `edge`).
-// Operation sequence of multicubic/regular.rs:474-623 + mod.rs:72-91, with these fusions, each of which returns the
-// bits of the two-operation original because its inner product is exact (a power-of-two scaling; needs the scaled
-// value to stay normal, i.e. grid-value differences within [2^-1021, 2^1023]):
+// fl bit 0|1 = this lane is in an end cell (k1 is the natural-spline slope), bit 2 = outside the grid with
+// linearize_extrapolation; `all_none` is warp-uniform (no lane of the warp is in an end cell).
+// Regular grids: operation sequence of multicubic/regular.rs:474-623 + mod.rs:72-91, with these fusions, each of which
+// returns the bits of the two-operation original because its inner product is exact (a power-of-two scaling; needs
+// the scaled value to stay normal, i.e. grid-value differences within [2^-1021, 2^1023]):
 //   a  = (v2-v0)/2 - dy      -> fma(0.5, v2-v0, -dy)
 //   b  = -(v3-v1)/2 + dy     -> fma(-0.5, v3-v1, dy)
 //   c2 = b - (a+a)           -> fma(-2, a, b)
 //   k1 = 2*dy - k0           -> fma(2, dy, -k0)
 template <class T>
-__device__ __forceinline__ T cubic_step_perm(T u0, T u1, T u2, T u3, T tt, bool edge, bool lin, bool all_none) {
+__device__ __forceinline__ T cubic_step_perm(T u0, T u1, T u2, T u3, const QuadDim<T, false>& c, int fl, bool all_none) {
     using O = Ops<T>;
     const T half = T(0.5), two = T(2);
+    const T tt = c.tt;
     const T d20 = O::sub(u2, u0);
     const T dy = O::sub(u2, u1);
     const T a = O::fma(half, d20, -dy);
@@ -60,26 +116,45 @@ __device__ __forceinline__ T cubic_step_perm(T u0, T u1, T u2, T u3, T tt, bool 
     const T k0 = O::mul(d20, half);
     const T knat = O::fma(two, dy, -k0);
     const T kint = O::mul(O::sub(u3, u1), half);
-    const T k1 = edge ? knat : kint;
+    const T k1 = (fl & 3) ? knat : kint;
     const T b = O::sub(dy, k1);
     const T c1 = O::add(dy, a);
     const T c2 = O::fma(-two, a, b);
     const T c3 = O::sub(a, b);
     const T cub = O::add(u1, O::mul(tt, O::add(c1, O::mul(tt, O::add(c2, O::mul(tt, c3))))));
     const T linv = O::add(u2, O::mul(k1, O::sub(tt, T(1))));
-    return lin ? linv : cub;
+    return (fl & 4) ? linv : cub;
+}
+
+// Rectilinear grids (multicubic/rectilinear.rs:413-545, mod.rs:103-117). On permuted inputs every class has
+//   k0 = wa*(u2-u1) + wc*((u1-u0)/div0),   dy = u2-u1,   y0 = u1
+// (interior: as written; high end: the same expression on (v1,v2,v3); low end: -(wa*((v2-v1)/q) + wc*(v1-v0)) equals
+// wc*(u2-u1) + wa*((u1-u0)/q) on (v2,v1,v0) because negation commutes with every rounding — hence the exchanged
+// weights), and k1 is the interior slope wa1*((u3-u2)/div1) + wc1*(u2-u1) or the end slope 2*dy - k0.
+template <class T>
+__device__ __forceinline__ T cubic_step_perm(T u0, T u1, T u2, T u3, const QuadDim<T, true>& c, int fl, bool all_none) {
+    using O = Ops<T>;
+    const bool fast = (fl & 8) != 0;
+    const T d10 = O::sub(u1, u0), dy = O::sub(u2, u1), d32 = O::sub(u3, u2);
+    const T k0 = O::add(O::mul(c.wa, dy), O::mul(c.wc, exact_div(d10, c.div0, c.rdiv0, fast)));
+    const T kint = O::add(O::mul(c.wa1, exact_div(d32, c.div1, c.rdiv1, fast)), O::mul(c.wc1, dy));
+    if (all_none) return hermite_fused(c.tt, u1, dy, k0, kint);
+    const T k1 = (fl & 3) ? O::fma(T(2), dy, -k0) : kint;
+    const T cub = hermite_fused(c.tt, u1, dy, k0, k1);
+    const T linv = O::add(u2, O::mul(k1, O::sub(c.tt, T(1))));
+    return (fl & 4) ? linv : cub;
 }
 
 // The same step on inputs in natural order: the permutation is done with selects (dimension N-2, whose four inputs
 // sit in one sector).
-template <class T>
-__device__ __forceinline__ T cubic_step_sel(T v0, T v1, T v2, T v3, T tt, int mode, bool lin, bool all_none) {
-    if (all_none) return cubic_step_perm(v0, v1, v2, v3, tt, false, false, true);
-    const bool low = mode == kModeLow, high = mode == kModeHigh;
+template <class T, bool RECT>
+__device__ __forceinline__ T cubic_step_sel(T v0, T v1, T v2, T v3, const QuadDim<T, RECT>& c, int fl, bool all_none) {
+    if (all_none) return cubic_step_perm(v0, v1, v2, v3, c, fl, true);
+    const bool low = (fl & 3) == kModeLow, high = (fl & 3) == kModeHigh;
     const T u0 = low ? v2 : (high ? v1 : v0);
     const T u1 = high ? v2 : v1;
     const T u2 = low ? v0 : (high ? v3 : v2);
-    return cubic_step_perm(u0, u1, u2, v3, tt, low || high, lin, false);
+    return cubic_step_perm(u0, u1, u2, v3, c, fl, false);
 }
 
 // Row (or lane) order of the permuted inputs: interior 0,1,2,3; low end 2,1,0,3; high end 1,2,3,3.
@@ -91,9 +166,9 @@ __device__ __forceinline__ void cubic_perm(int mode, int (&k)[4]) {
     k[3] = 3;
 }
 
-// Cell location of one point on every dimension (ref: multicubic/regular.rs:432-469 and :356-360).
+// Cell location of one point on every dimension, regular grid (ref: multicubic/regular.rs:432-469 and :356-360).
 template <class T, int N>
-__device__ __forceinline__ bool quad4_locate(const EvalArgs<T, N>& a, const T (&x)[N], QuadSlot<T, N>& s) {
+__device__ __forceinline__ bool quad4_locate(const EvalArgs<T, N>& a, const T*, const T (&x)[N], QuadSlot<T, N, false>& s) {
     using O = Ops<T>;
     bool ok = true;
     int base = 0, flags = 0;
@@ -123,109 +198,180 @@ __device__ __forceinline__ bool quad4_locate(const EvalArgs<T, N>& a, const T (&
         const T t = exact_div(O::sub(x[d], x1), a.step[d], a.rstep[d], a.fast_div != 0);
         s.tt[d] = mode == kModeNone ? t : (mode == kModeLow ? -t : O::sub(t, T(1)));
         base += origin * a.istride[d];
-        flags |= (mode | ((outside && a.linearize) ? 4 : 0)) << (3 * d);
+        flags |= (mode | ((outside && a.linearize) ? 4 : 0)) << (4 * d);
     }
     s.base = base;
     s.flags = flags;
     return ok;
 }
 
+// Rectilinear grid (ref: multicubic/rectilinear.rs:366-408): never fails, NaN lands in the first cell. The cell's
+// class, reference node and width come from the cell table; t = +-(x - gref)/href is the reference's division
+// (kernels.cuh cubic_rect_locate) through the tabulated reciprocal (device_math.cuh exact_div).
+template <class T, int N>
+__device__ __forceinline__ bool quad4_locate(const EvalArgs<T, N>& a, const T* __restrict__ axes, const T (&x)[N],
+                                             QuadSlot<T, N, true>& s) {
+    using O = Ops<T>;
+    int base = 0, flags = 0;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+        const int pp = rect_lower_bound<T, N>(a, axes, d, x[d]);
+        const T* row = axes + a.ct_off[d] + pp * kCubicCellRow;
+        const T gref = row[8], href = row[9], rhref = row[10];
+        int rf;
+        if constexpr (sizeof(T) == 8) rf = __double2loint(row[11]);
+        else rf = __float_as_int(row[11]);
+        const T e = O::sub(x[d], gref);
+        s.tt[d] = exact_div((rf & 3) == kModeLow ? -e : e, href, rhref, (rf & 16) != 0);
+        s.pp[d] = pp;
+        base += clamp_cell(pp - 2, a.dim[d] - 4) * a.istride[d];
+        flags |= ((rf & 3) | (((rf & 4) && a.linearize) ? 4 : 0) | (rf & 8)) << (4 * d);
+    }
+    s.base = base;
+    s.flags = flags;
+    return true;
+}
+
+// k-th input of a step in permuted order: interior 0,1,2,3; low end 2,1,0,3; high end 1,2,3,3.
+__device__ __forceinline__ int cubic_perm_k(int mode, int k) {
+    return mode == kModeLow ? (k < 3 ? 2 - k : 3) : (mode == kModeHigh ? min(k + 1, 3) : k);
+}
+
 // Reduces dimensions 0..D-1 (address dimensions, D <= N-2) of the sub-block at sector index `idx` for the four
-// in-sector positions at once. ro[d][k] = offset of the k-th permuted row of dimension d.
-template <int D, class T, int N>
-__device__ __forceinline__ void quad4_rows(const T* __restrict__ win, int idx, const int (&ro)[N][4], const T (&tt)[N],
-                                           int flags, unsigned none_mask, T (&out)[4]) {
+// in-sector positions at once; the rows of each dimension are visited in the permuted order of its saturation class.
+// The per-dimension parameters are read from the owner's slot (and the cell table) where they are used, so they are
+// live only for the steps of their dimension.
+template <int D, class T, int N, bool RECT>
+__device__ __forceinline__ void quad4_rows(const EvalArgs<T, N>& a, const T* __restrict__ axes, int idx,
+                                           const QuadSlot<T, N, RECT>* sp, int flags, unsigned none_mask, T (&out)[4]) {
     if constexpr (D == 0) {
-        load_row<T, 4, true, int>(nullptr, win, idx, out);
+        load_row<T, 4, true, int>(nullptr, a.win, idx, out);
     } else {
+        const int fl = flags >> (4 * (D - 1));
+        const bool all_none = (none_mask >> (D - 1)) & 1u;
+        const int mode = all_none ? 0 : (fl & 3), stride = a.istride[D - 1];
         T sub[4][4];
+        if constexpr (D >= 2) {
+            // Not unrolled (code size: a 4-D footprint unrolled 16 ways did not fit the instruction cache). The four
+            // partial rows are shifted through `sub` so that no register array is indexed dynamically.
+#pragma unroll 1
+            for (int k = 0; k < 4; ++k) {
+                T rk[4];
+                quad4_rows<D - 1, T, N, RECT>(a, axes, idx + cubic_perm_k(mode, k) * stride, sp, flags, none_mask, rk);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) quad4_rows<D - 1, T, N>(win, idx + ro[D - 1][k], ro, tt, flags, none_mask, sub[k]);
-        const int fl = flags >> (3 * (D - 1));
-        const bool edge = (fl & 3) != 0, lin = (fl & 4) != 0, all_none = (none_mask >> (D - 1)) & 1u;
-        if (all_none) {  // one warp-uniform branch around the four independent steps: they interleave
-#pragma unroll
-            for (int j = 0; j < 4; ++j) out[j] = cubic_step_perm(sub[0][j], sub[1][j], sub[2][j], sub[3][j], tt[D - 1], false, false, true);
+                for (int j = 0; j < 4; ++j) {
+                    sub[0][j] = sub[1][j]; sub[1][j] = sub[2][j]; sub[2][j] = sub[3][j]; sub[3][j] = rk[j];
+                }
+            }
         } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) out[j] = cubic_step_perm(sub[0][j], sub[1][j], sub[2][j], sub[3][j], tt[D - 1], edge, lin, false);
+            for (int k = 0; k < 4; ++k)
+                quad4_rows<D - 1, T, N, RECT>(a, axes, idx + cubic_perm_k(mode, k) * stride, sp, flags, none_mask, sub[k]);
+        }
+        const QuadDim<T, RECT> c = quad4_dim<T, N>(a, axes, sp, D - 1);
+        if (all_none) {  // one warp-uniform branch around the four independent steps: they interleave
+#pragma unroll
+            for (int j = 0; j < 4; ++j) out[j] = cubic_step_perm(sub[0][j], sub[1][j], sub[2][j], sub[3][j], c, fl, true);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) out[j] = cubic_step_perm(sub[0][j], sub[1][j], sub[2][j], sub[3][j], c, fl, false);
         }
     }
 }
 
-template <class T, int N, int MINB>
+template <class T, int N, bool RECT>
+__host__ __device__ constexpr int quad4_slot_warp_bytes() {  // one slot per lane + 16 bytes of padding per quad (bank spreading)
+    return 32 * static_cast<int>(sizeof(QuadSlot<T, N, RECT>)) + 8 * 16;
+}
+constexpr int kQuad4XposeQuad = 20;  // transposition buffer [quad][lane j][point p]: quad stride 16 + 4 elements
+template <class T, int N, bool RECT>
+__host__ __device__ constexpr size_t quad4_smem_bytes() {  // beyond the staged axes
+    return static_cast<size_t>(kBlock / 32) * (quad4_slot_warp_bytes<T, N, RECT>() + 8 * kQuad4XposeQuad * sizeof(T));
+}
+
+template <class T, int N, bool RECT, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB) cubic_quad4_kernel(const __grid_constant__ EvalArgs<T, N> a) {
     static_assert(N >= 2 && N <= 4, "quad-cooperative cubic covers N = 2..4");
-    using Slot = QuadSlot<T, N>;
+    using Slot = QuadSlot<T, N, RECT>;
     constexpr int kWarps = kBlock / 32;
-    // Parameter slots: one per lane, 16 bytes of padding per quad so that the eight quads of a warp read eight
-    // different bank groups. Transposition buffer: [quad][lane j][point p], quad stride 16 + 4 elements.
-    constexpr int kSlotWarpBytes = 32 * static_cast<int>(sizeof(Slot)) + 8 * 16;
-    constexpr int kXposeQuad = 20;
-    __shared__ __align__(16) unsigned char s_slots[kWarps * kSlotWarpBytes];
-    __shared__ __align__(16) T s_xpose[kWarps * 8 * kXposeQuad];
+    constexpr int kUnrollP = (!RECT && N <= 3) ? 4 : 1;
+    constexpr int kSlotWarpBytes = quad4_slot_warp_bytes<T, N, RECT>();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const T* axes = nullptr;
+    size_t axes_bytes = 0;
+    if constexpr (RECT) {
+        axes = stage_axes<T, N>(a);
+        if (a.axes_in_smem) axes_bytes = (static_cast<size_t>(a.axes_total) * sizeof(T) + 15) / 16 * 16;
+    }
+    unsigned char* s_slots = smem_raw + axes_bytes;
+    T* s_xpose = reinterpret_cast<T*>(s_slots + kWarps * kSlotWarpBytes);
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, b = lane & 3u, quad = lane >> 2;
-    unsigned char* wslots = s_slots + warp * kSlotWarpBytes;
-    Slot* myslot = reinterpret_cast<Slot*>(wslots + lane * sizeof(Slot) + quad * 16);
-    T* xq = s_xpose + (warp * 8 + quad) * kXposeQuad;
+    unsigned char* wslots = s_slots + warp * kSlotWarpBytes + quad * 16;
+    Slot* myslot = reinterpret_cast<Slot*>(wslots) + lane;
+    const Slot* qslots = reinterpret_cast<const Slot*>(wslots) + (lane & ~3u);
+    T* xq = s_xpose + (warp * 8 + quad) * kQuad4XposeQuad;
 
+    // The coordinates of the NEXT block of points are requested after the last gather of the current one has been
+    // consumed (its registers are free again), so their DRAM latency overlaps the transposition, the final step
+    // and the store instead of stalling the next cell location.
     BlockSchedule sched;
-    while (sched.next(a.work, a.n)) {
-        const unsigned long long i = sched.blk * blockDim.x + threadIdx.x;
-        const bool valid = i < a.n;
-        const unsigned long long il = valid ? i : a.n - 1;
-        T x[N];
+    if (!sched.next(a.work, a.n)) return;
+    unsigned long long i = sched.blk * blockDim.x + threadIdx.x;
+    bool valid = i < a.n;
+    T x[N];
 #pragma unroll
-        for (int d = 0; d < N; ++d) x[d] = load_query(a.obs[d] + il);
-        Slot mine;
-        const bool ok = quad4_locate<T, N>(a, x, mine);
-        if (!ok) mine.base = 0;  // keep the gathers in range; the result is discarded
-        *myslot = mine;
+    for (int d = 0; d < N; ++d) x[d] = load_query(a.obs[d] + (valid ? i : a.n - 1));
+    for (;;) {
+        bool ok;
         unsigned edges[N];  // lanes (= points) of the warp that are in an end cell of dimension d
+        {
+            Slot mine;
+            ok = quad4_locate<T, N>(a, axes, x, mine);
+            if (!ok) mine.base = 0;  // keep the gathers in range; the result is discarded
+            *myslot = mine;
 #pragma unroll
-        for (int d = 0; d < N; ++d) edges[d] = __ballot_sync(0xffffffffu, ((mine.flags >> (3 * d)) & 3) != 0);
+            for (int d = 0; d < N; ++d) edges[d] = __ballot_sync(0xffffffffu, ((mine.flags >> (4 * d)) & 3) != 0);
+        }
         __syncwarp();
 
-        T s[4];
-#pragma unroll
+        // The four points of the quad, one after the other. Each lane's partial result goes straight into the
+        // transposition buffer [lane j][point p]; unrolled only where the body is small (IB200_QUAD4_UNROLL).
+#pragma unroll(kUnrollP)
         for (int p = 0; p < 4; ++p) {
-            const Slot sp = *reinterpret_cast<const Slot*>(wslots + ((lane & ~3u) + p) * sizeof(Slot) + quad * 16);
+            const Slot* sp = qslots + p;
+            const int flags = sp->flags;
             unsigned none_mask = 0;
 #pragma unroll
             for (int d = 0; d < N; ++d) none_mask |= (edges[d] & (0x11111111u << p)) == 0u ? (1u << d) : 0u;
-            int ro[N][4];
-#pragma unroll
-            for (int d = 0; d + 2 < N; ++d) {
-                if ((none_mask >> d) & 1u) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) ro[d][k] = k * a.istride[d];
-                } else {
-                    int k4[4];
-                    cubic_perm((sp.flags >> (3 * d)) & 3, k4);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) ro[d][k] = k4[k] * a.istride[d];
-                }
-            }
             T r[4];
-            quad4_rows<N - 2, T, N>(a.win, sp.base + static_cast<int>(b), ro, sp.tt, sp.flags, none_mask, r);
-            const int fl = sp.flags >> (3 * (N - 2));
-            s[p] = cubic_step_sel(r[0], r[1], r[2], r[3], sp.tt[N - 2], fl & 3, (fl & 4) != 0, (none_mask >> (N - 2)) & 1u);
+            quad4_rows<N - 2, T, N, RECT>(a, axes, sp->base + static_cast<int>(b), sp, flags, none_mask, r);
+            const QuadDim<T, RECT> c = quad4_dim<T, N>(a, axes, sp, N - 2);
+            xq[b * 4 + p] = cubic_step_sel<T, RECT>(r[0], r[1], r[2], r[3], c, flags >> (4 * (N - 2)), (none_mask >> (N - 2)) & 1u);
+        }
+        const unsigned long long i_cur = i;
+        const bool valid_cur = valid;
+        const bool more = sched.next(a.work, a.n);
+        if (more) {
+            i = sched.blk * blockDim.x + threadIdx.x;
+            valid = i < a.n;
+#pragma unroll
+            for (int d = 0; d < N; ++d) x[d] = load_query(a.obs[d] + (valid ? i : a.n - 1));
         }
         // Transposition: lane j holds the partial results of its last-dimension node for points 0..3; the owner of
         // point b needs the four nodes' results of point b, in the permuted order of its saturation class.
-#pragma unroll
-        for (int p = 0; p < 4; ++p) xq[b * 4 + p] = s[p];
         __syncwarp();
-        const int fl = mine.flags >> (3 * (N - 1));
+        const int fl = myslot->flags >> (4 * (N - 1));  // re-read from the slot: not kept live across the point loop
         int k4[4];
         cubic_perm(fl & 3, k4);
         const T w0 = xq[k4[0] * 4 + b], w1 = xq[k4[1] * 4 + b], w2 = xq[k4[2] * 4 + b], w3 = xq[12 + b];
-        const T res = cubic_step_perm(w0, w1, w2, w3, mine.tt[N - 1], (fl & 3) != 0, (fl & 4) != 0, edges[N - 1] == 0u);
+        const QuadDim<T, RECT> c = quad4_dim<T, N>(a, axes, myslot, N - 1);
+        const T res = cubic_step_perm(w0, w1, w2, w3, c, fl, edges[N - 1] == 0u);
         __syncwarp();  // the next iteration overwrites both buffers
-        if (valid) {
-            if (ok) store_result(a.out + i, res);
-            else report_bad(a, i);
+        if (valid_cur) {
+            if (ok) store_result(a.out + i_cur, res);
+            else report_bad(a, i_cur);
         }
+        if (!more) break;
     }
 }
 

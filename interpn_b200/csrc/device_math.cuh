@@ -95,15 +95,18 @@ __device__ __forceinline__ bool exact_div_exponent_ok(double v) {
 __device__ __forceinline__ bool exact_div_divisor_ok(double b) { return exact_div_exponent_ok(b); }
 __device__ __forceinline__ bool exact_div_divisor_ok(float) { return false; }
 
+// The IEEE division of the rare operands outside the guarded range, out of line: inlined, its ~40 instructions per
+// call site made the cubic kernels overflow the instruction cache (ncu: 6 "no instruction" stall cycles per issue).
+static __device__ __noinline__ double exact_div_slow(double a, double b) { return __ddiv_rn(a, b); }
+
 __device__ __forceinline__ double exact_div(double a, double b, double rb, bool divisor_ok) {
-    if (divisor_ok && exact_div_exponent_ok(a)) {
-        const double q0 = __dmul_rn(a, rb);
-        const double e0 = __fma_rn(-q0, b, a);
-        const double q1 = __fma_rn(e0, rb, q0);
-        const double e1 = __fma_rn(-q1, b, a);
-        return __fma_rn(e1, rb, q1);
-    }
-    return __ddiv_rn(a, b);
+    const double q0 = __dmul_rn(a, rb);
+    const double e0 = __fma_rn(-q0, b, a);
+    const double q1 = __fma_rn(e0, rb, q0);
+    const double e1 = __fma_rn(-q1, b, a);
+    double q = __fma_rn(e1, rb, q1);
+    if (!(divisor_ok && exact_div_exponent_ok(a))) q = exact_div_slow(a, b);
+    return q;
 }
 __device__ __forceinline__ float exact_div(float a, float b, float, bool) { return __fdiv_rn(a, b); }
 

@@ -36,6 +36,8 @@ struct DeviceGrid {
     int lut_off[kMaxNd] = {};       // element offset of axis d's bucket table (lut_nb+1 ints)
     int lut_nb[kMaxNd] = {};
     double lut_scale[kMaxNd] = {};  // buckets per unit length
+    int rect_cubic_table = 0;       // cubic, strictly increasing finite axes: per-cell constant table present
+    int ct_off[kMaxNd] = {};        // element offset of axis d's cubic cell table (dim+1 rows of 12 elements, 16-byte aligned)
     int sm_count = 148;
 };
 

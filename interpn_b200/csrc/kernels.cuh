@@ -32,6 +32,8 @@ struct EvalArgs {
     int axes_total;   // rectilinear: elements of the blob (axes, reciprocal cell widths, bucket tables)
     int rect_fast, rect_fast_div;  // rectilinear: search / division accelerators are valid (capi.cu rect_new)
     int rc_off[N], lut_off[N], lut_nb[N];
+    int ct_off[N];  // rectilinear cubic: per-cell constant tables (capi.cu cubic_cell_table), valid when rect_cubic_table
+    int rect_cubic_table;
     T lut_scale[N];
     int axes_in_smem;
     int linearize;

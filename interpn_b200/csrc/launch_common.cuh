@@ -28,6 +28,7 @@ inline EvalArgs<T, N> make_args(const DeviceGrid& g, const T* const* obs, size_t
         a.rc_off[d] = g.rc_off[d];
         a.lut_off[d] = g.lut_off[d];
         a.lut_nb[d] = g.lut_nb[d];
+        a.ct_off[d] = g.ct_off[d];
         a.lut_scale[d] = static_cast<T>(g.lut_scale[d]);
     }
     a.out = out;
@@ -50,6 +51,7 @@ inline EvalArgs<T, N> make_args(const DeviceGrid& g, const T* const* obs, size_t
     a.axes_total = g.axes_total;
     a.rect_fast = g.rect_fast;
     a.rect_fast_div = g.rect_fast_div;
+    a.rect_cubic_table = g.rect_cubic_table;
     a.axes_in_smem = g.rect && static_cast<size_t>(g.axes_total) * sizeof(T) <= kAxesSmemBudget;
     a.linearize = g.linearize;
     a.first_bad = first_bad;
@@ -95,6 +97,7 @@ struct LaunchOpts {
     int threads_per_point = 1;           // 4 for the quad-cooperative kernels
     bool window = false;                 // the kernel gathers from the window copy, not from vals
     int ctas_per_sm = 8;
+    size_t extra_smem = 0;               // dynamic shared memory beyond the staged axes (cubic_quad4.cuh)
 };
 
 template <class T, int N, class K>
@@ -105,6 +108,7 @@ inline cudaError_t launch_generic(K kernel, const DeviceGrid& g, const T* const*
     const int points_per_thread = o.points_per_thread, threads_per_point = o.threads_per_point, ctas_per_sm = o.ctas_per_sm;
     EvalArgs<T, N> a = make_args<T, N>(g, obs, n, out, first_bad, index_base, o.remap, o.work);
     size_t smem = a.axes_in_smem ? static_cast<size_t>(g.axes_total) * sizeof(T) : 0;
+    if (o.extra_smem) smem = (smem + 15) / 16 * 16 + o.extra_smem;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;

@@ -1,5 +1,8 @@
 // launch_cubic_rect.cu — multicubic rectilinear-grid launchers (f32/f64, N = 1..8).
+#include <type_traits>
+
 #include "sweep.cuh"
+#include "cubic_quad4.cuh"
 
 namespace ib200 {
 
@@ -24,11 +27,38 @@ cudaError_t launch_cubic_rect(const DeviceGrid& g, const T* const* obs, size_t n
         if (win && g.ndims == 1) {
             e = launch_generic<T, 1>(cubic_kernel<T, 1, true, true, 1>, g, o, cnt, dst, first_bad, base, stream, lo(1, true));
         } else if (win) {
-            switch (g.ndims) {
-                case 2: e = launch_generic<T, 2>(cubic_quad_kernel<T, 2, true, IB200_MINB_QUAD2>, g, o, cnt, dst, first_bad, base, stream, lo(4, true)); break;
-                case 3: e = launch_generic<T, 3>(cubic_quad_kernel<T, 3, true, IB200_MINB_QUAD3_RECT>, g, o, cnt, dst, first_bad, base, stream, lo(4, true)); break;
-                case 4: e = launch_generic<T, 4>(cubic_quad_kernel<T, 4, true, IB200_MINB_QUAD4>, g, o, cnt, dst, first_bad, base, stream, lo(4, true)); break;
-                default: break;
+            // Four points per quad (cubic_quad4.cuh); INTERPN_B200_CUBIC_QUAD=1 selects the one-point-per-quad
+            // kernel of kernels.cuh, INTERPN_B200_QUAD4_MINB the register budget (CTAs per SM) for tuning runs.
+            static const int variant = static_cast<int>(sweep_env("INTERPN_B200_CUBIC_QUAD", 4));
+            static const int minb = static_cast<int>(sweep_env("INTERPN_B200_QUAD4_MINB", 0));
+            if (variant == 4 && g.rect_cubic_table) {  // the cell table exists for strictly increasing finite axes
+                auto q4 = [&](auto kernel, auto ntag) {
+                    constexpr int N = decltype(ntag)::value;
+                    LaunchOpts r = lo(1, true);
+                    r.extra_smem = quad4_smem_bytes<T, N, true>();
+                    return launch_generic<T, N>(kernel, g, o, cnt, dst, first_bad, base, stream, r);
+                };
+                using std::integral_constant;
+                switch (g.ndims) {
+                    case 2: e = q4(cubic_quad4_kernel<T, 2, true, 3>, integral_constant<int, 2>()); break;
+                    case 3:
+                        if (minb == 3) e = q4(cubic_quad4_kernel<T, 3, true, 3>, integral_constant<int, 3>());
+                        else e = q4(cubic_quad4_kernel<T, 3, true, 2>, integral_constant<int, 3>());
+                        break;
+                    case 4:
+                        if (minb == 3) e = q4(cubic_quad4_kernel<T, 4, true, 3>, integral_constant<int, 4>());
+                        else if (minb == 1) e = q4(cubic_quad4_kernel<T, 4, true, 1>, integral_constant<int, 4>());
+                        else e = q4(cubic_quad4_kernel<T, 4, true, 2>, integral_constant<int, 4>());
+                        break;
+                    default: break;
+                }
+            } else {
+                switch (g.ndims) {
+                    case 2: e = launch_generic<T, 2>(cubic_quad_kernel<T, 2, true, IB200_MINB_QUAD2>, g, o, cnt, dst, first_bad, base, stream, lo(4, true)); break;
+                    case 3: e = launch_generic<T, 3>(cubic_quad_kernel<T, 3, true, IB200_MINB_QUAD3_RECT>, g, o, cnt, dst, first_bad, base, stream, lo(4, true)); break;
+                    case 4: e = launch_generic<T, 4>(cubic_quad_kernel<T, 4, true, IB200_MINB_QUAD4>, g, o, cnt, dst, first_bad, base, stream, lo(4, true)); break;
+                    default: break;
+                }
             }
         } else {
             IB200_SWITCH_N(8, e = (launch_generic<T, N>(cubic_kernel<T, N, true, false, cubic_min_blocks<N, true>()>, g, o, cnt, dst, first_bad, base, stream, lo(1, false)));)

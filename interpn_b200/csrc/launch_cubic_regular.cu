@@ -1,4 +1,6 @@
 // launch_cubic_regular.cu — multicubic regular-grid launchers (f32/f64, N = 1..8).
+#include <type_traits>
+
 #include "sweep.cuh"
 #include "cubic_quad4.cuh"
 
@@ -30,16 +32,22 @@ cudaError_t launch_cubic_regular(const DeviceGrid& g, const T* const* obs, size_
             static const int variant = static_cast<int>(sweep_env("INTERPN_B200_CUBIC_QUAD", 4));
             static const int minb = static_cast<int>(sweep_env("INTERPN_B200_QUAD4_MINB", 0));
             if (variant == 4) {
+                auto q4 = [&](auto kernel, auto ntag) {
+                    constexpr int N = decltype(ntag)::value;
+                    LaunchOpts r = lo(1, true);
+                    r.extra_smem = quad4_smem_bytes<T, N, false>();
+                    return launch_generic<T, N>(kernel, g, o, cnt, dst, first_bad, base, stream, r);
+                };
+                using std::integral_constant;
                 switch (g.ndims) {
-                    case 2: e = launch_generic<T, 2>(cubic_quad4_kernel<T, 2, 4>, g, o, cnt, dst, first_bad, base, stream, lo(1, true)); break;
+                    case 2: e = q4(cubic_quad4_kernel<T, 2, false, 4>, integral_constant<int, 2>()); break;
                     case 3:
-                        if (minb == 2) e = launch_generic<T, 3>(cubic_quad4_kernel<T, 3, 2>, g, o, cnt, dst, first_bad, base, stream, lo(1, true));
-                        else if (minb == 3) e = launch_generic<T, 3>(cubic_quad4_kernel<T, 3, 3>, g, o, cnt, dst, first_bad, base, stream, lo(1, true));
-                        else e = launch_generic<T, 3>(cubic_quad4_kernel<T, 3, 4>, g, o, cnt, dst, first_bad, base, stream, lo(1, true));
+                        if (minb == 3) e = q4(cubic_quad4_kernel<T, 3, false, 3>, integral_constant<int, 3>());
+                        else e = q4(cubic_quad4_kernel<T, 3, false, 4>, integral_constant<int, 3>());
                         break;
                     case 4:
-                        if (minb == 3) e = launch_generic<T, 4>(cubic_quad4_kernel<T, 4, 3>, g, o, cnt, dst, first_bad, base, stream, lo(1, true));
-                        else e = launch_generic<T, 4>(cubic_quad4_kernel<T, 4, 2>, g, o, cnt, dst, first_bad, base, stream, lo(1, true));
+                        if (minb == 3) e = q4(cubic_quad4_kernel<T, 4, false, 3>, integral_constant<int, 4>());
+                        else e = q4(cubic_quad4_kernel<T, 4, false, 2>, integral_constant<int, 4>());
                         break;
                     default: break;
                 }

@@ -241,8 +241,25 @@ def get(name: str, dtype=np.float64) -> Workload:
         return _rectilinear(name, "nearest", 2, 1024, dtype, 1_000_000_000, oob_fraction=0.05, plant_special=True)
     if name == "c5_nearest3d_rect128":
         return _rectilinear(name, "nearest", 3, 128, dtype, 1_000_000_000, oob_fraction=0.05, plant_special=True)
+    # Extra shapes on L2-resident grids (not BASELINE.json configurations): the same kernels on the other
+    # 3-D / 4-D method x grid-kind combinations, for parity at scale and for the per-kernel measurements.
+    if name == "x_linear3d_reg100":
+        return _regular(name, "linear", [100] * 3, [0.0] * 3, [100.0 / 99.0] * 3, dtype, 100_000_000, oob_fraction=0.10)
+    if name == "x_linear4d_reg32":
+        return _regular(name, "linear", [32] * 4, [0.0] * 4, [1.0] * 4, dtype, 100_000_000, oob_fraction=0.10)
+    if name == "x_cubic4d_reg32":
+        return _regular(name, "cubic", [32] * 4, [0.0] * 4, [1.0] * 4, dtype, 100_000_000,
+                        linearize=True, oob_fraction=0.10)  # fmt: skip
+    if name == "x_cubic3d_rect100":
+        return _rectilinear(name, "cubic", 3, 100, dtype, 100_000_000, linearize=True, oob_fraction=0.10)
+    if name == "x_cubic4d_rect32":
+        return _rectilinear(name, "cubic", 4, 32, dtype, 100_000_000, linearize=False, oob_fraction=0.10)
+    if name == "x_linear4d_rect32":
+        return _rectilinear(name, "linear", 4, 32, dtype, 100_000_000, oob_fraction=0.10)
     raise KeyError(name)
 
+
+EXTRA = ["x_linear3d_reg100", "x_linear4d_reg32", "x_cubic4d_reg32", "x_cubic3d_rect100", "x_cubic4d_rect32", "x_linear4d_rect32"]
 
 ALL = [
     "c1_linear3d_reg20",

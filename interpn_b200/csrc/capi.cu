@@ -268,7 +268,12 @@ int validate_interp(size_t ndims, const size_t* obs_lens, size_t nobs, size_t no
 // the upper bound (0 disables the layout).
 int window_width(const DeviceGrid& g) {
     int w = 0;
-    if (g.method == INTERPN_B200_LINEAR && g.ndims <= 6) w = 2;
+    if (g.method == INTERPN_B200_LINEAR && g.ndims <= 6) {
+        // N >= 2: 2x2 patches (4-fold copy), except for N <= 4 grids between 48 and 100 KB, whose 2-fold row-pair copy
+        // still fits L1 while the 4-fold one would not (C1's 20^3 grid: 137 vs 120 G points/s)
+        const size_t b = g.nvals * static_cast<size_t>(g.elem);
+        w = (g.ndims >= 2 && !(g.ndims <= 4 && b > (48u << 10) && b <= (100u << 10))) ? 4 : 2;
+    }
     if (g.method == INTERPN_B200_CUBIC && g.ndims <= 4) w = 4;
     if (!w) return 0;
     // Kept up to 8 GiB and a quarter of the free memory. Direct kernels gather from it only while it is
@@ -292,7 +297,8 @@ int upload_vals(interpn_b200_interp* h, const void* vals, int vals_location) {
     const size_t bytes = g.nvals * static_cast<size_t>(g.elem);
     CUDA_TRY(cudaMalloc(&g.vals, bytes ? bytes : 1));
     g.win_width = window_width(g);
-    g.win_cross = g.win_width == 4 && g.ndims >= 2;  // cubic N = 2..4: quad-cooperative kernels
+    // cubic N = 2..4: cross-window layout (quad-cooperative kernels); linear N >= 2: patch layout
+    g.win_cross = g.win_width == 4 && g.ndims >= 2;
     if (g.win_width) CUDA_TRY(cudaMalloc(&g.win, bytes * g.win_width));
     if (vals_location == INTERPN_B200_VALS_UNINIT) return INTERPN_B200_OK;
     if (!vals) return INTERPN_B200_ERR_INVALID_ARG;

@@ -208,6 +208,47 @@ __device__ __forceinline__ void linear_rows(const T* __restrict__ vals, const T*
     }
 }
 
+// Patch layout (multilinear, N >= 2): pwin[f*4 + 2*i + j] = vals[f + i*D_{N-1} + j] — the 32-byte sector (f64) at flat
+// index f holds the 2x2 patch of the last two dimensions that starts at f, so a footprint is 2^(N-2) sectors = L1
+// wavefronts instead of 2^(N-1) rows (the multilinear kernels on L2-resident grids sit on the L1 wavefront rate,
+// DESIGN.md §4.1). Reduces dimensions 0..D-1 for the four patch positions at once; the caller finishes with
+// dimension N-2 (between the patch's two rows) and N-1, so every lerp and their order are the reference's.
+template <int D, class T, int N, class I>
+__device__ __forceinline__ void linear_patches(const T* __restrict__ win, I idx, const I (&stride)[N], const T (&t)[N],
+                                               T (&out)[4]) {
+    using O = Ops<T>;
+    if constexpr (D == 0) {
+        load_row<T, 4, true, I>(nullptr, win, idx, out);
+    } else {
+        T lo[4], hi[4];
+        linear_patches<D - 1, T, N, I>(win, idx, stride, t, lo);
+        linear_patches<D - 1, T, N, I>(win, idx + stride[D - 1], stride, t, hi);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out[j] = O::add(lo[j], O::mul(t[D - 1], O::sub(hi[j], lo[j])));
+    }
+}
+
+// The whole lerp tree of one located point. WL = layout gathered from: 0 the grid itself, 2 the row-pair window copy,
+// 4 the 2x2 patch copy.
+template <class T, int N, int WL, class I>
+__device__ __forceinline__ T linear_tree(const T* __restrict__ vals, const T* __restrict__ win, I base,
+                                         const I (&stride)[N], const T (&t)[N]) {
+    using O = Ops<T>;
+    constexpr bool WIN = WL != 0;
+    if constexpr (WL == 4) {
+        static_assert(N >= 2, "the patch layout needs two dimensions");
+        T v[4];
+        linear_patches<N - 2, T, N, I>(win, base, stride, t, v);
+        const T r0 = O::add(v[0], O::mul(t[N - 2], O::sub(v[2], v[0])));
+        const T r1 = O::add(v[1], O::mul(t[N - 2], O::sub(v[3], v[1])));
+        return O::add(r0, O::mul(t[N - 1], O::sub(r1, r0)));
+    } else {
+        T r[2];
+        linear_rows<N - 1, T, N, WIN, I>(vals, win, base, stride, t, r);
+        return O::add(r[0], O::mul(t[N - 1], O::sub(r[1], r[0])));
+    }
+}
+
 // Locate one query point: per-dimension cell origin -> flat index of the footprint's first corner,
 // and the normalized coordinates t. Returns false for an unrepresentable coordinate (regular grids).
 template <class T, int N, bool RECT, class I>
@@ -350,7 +391,7 @@ __device__ __forceinline__ bool nearest_locate_any(const EvalArgs<T, N>& a, cons
 // coordinate array, P independent locate/gather chains in flight, one vector store. The host picks
 // P > 1 only when every coordinate array and `out` are P*sizeof(T)-aligned (launch_common.cuh); the
 // n % P tail is evaluated one point per thread.
-template <class T, int N, bool RECT, bool WIN, int P, class I>
+template <class T, int N, bool RECT, int WL, int P, class I>
 __global__ void __launch_bounds__(kBlock) linear_kernel(const __grid_constant__ EvalArgs<T, N> a) {
     using O = Ops<T>;
     const I(&stride)[N] = strides_of<I>(a);
@@ -381,9 +422,7 @@ __global__ void __launch_bounds__(kBlock) linear_kernel(const __grid_constant__ 
             ok[p] = linear_locate_any<T, N, RECT, I>(a, axes, xs[p], t, base);
             all_ok = all_ok && ok[p];
             if (!ok[p]) base = 0;  // keep the gather in range; the value is discarded
-            T r[2];
-            linear_rows<N - 1, T, N, WIN, I>(a.vals, a.win, base, stride, t, r);
-            res[p] = O::add(r[0], O::mul(t[N - 1], O::sub(r[1], r[0])));
+            res[p] = linear_tree<T, N, WL, I>(a.vals, a.win, base, stride, t);
         }
         if (all_ok) {
             store_result_vec<T, P>(a.out + i0, res);
@@ -404,9 +443,7 @@ __global__ void __launch_bounds__(kBlock) linear_kernel(const __grid_constant__ 
             T t[N];
             I base;
             if (linear_locate_any<T, N, RECT, I>(a, axes, xs, t, base)) {
-                T r[2];
-                linear_rows<N - 1, T, N, WIN, I>(a.vals, a.win, base, stride, t, r);
-                store_result(a.out + i, O::add(r[0], O::mul(t[N - 1], O::sub(r[1], r[0]))));
+                store_result(a.out + i, linear_tree<T, N, WL, I>(a.vals, a.win, base, stride, t));
             } else {
                 report_bad(a, i);
             }

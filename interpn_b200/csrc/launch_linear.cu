@@ -4,7 +4,7 @@
 namespace ib200 {
 
 // The ordinary (direct) kernels. `remap` is set by the bin-swept path, which runs them on sorted coordinates.
-template <class T, int N, bool RECT, bool WIN>
+template <class T, int N, bool RECT, int WL>
 cudaError_t launch_linear_direct(const DeviceGrid& g, const T* const* obs, size_t n, T* out, unsigned long long* first_bad,
                                  unsigned long long index_base, cudaStream_t stream, const unsigned* remap,
                                  unsigned long long* work) {
@@ -14,40 +14,47 @@ cudaError_t launch_linear_direct(const DeviceGrid& g, const T* const* obs, size_
         o.points_per_thread = ppt;
         o.remap = remap;
         o.work = work;
-        o.window = WIN;
+        o.window = WL != 0;
         return o;
     };
     if (g.nvals >= (size_t(1) << 31))  // 64-bit index arithmetic: the basic kernel only
-        return launch_generic<T, N>(linear_kernel<T, N, RECT, false, 1, long long>, g, obs, n, out, first_bad, index_base, stream, opts(1));
+        return launch_generic<T, N>(linear_kernel<T, N, RECT, 0, 1, long long>, g, obs, n, out, first_bad, index_base, stream, opts(1));
     if (P > 1 && n >= static_cast<size_t>(P) && vector_aligned<T>(obs, N, out, P))
-        return launch_generic<T, N>(linear_kernel<T, N, RECT, WIN, P, int>, g, obs, n, out, first_bad, index_base, stream, opts(P));
-    return launch_generic<T, N>(linear_kernel<T, N, RECT, WIN, 1, int>, g, obs, n, out, first_bad, index_base, stream, opts(1));
+        return launch_generic<T, N>(linear_kernel<T, N, RECT, WL, P, int>, g, obs, n, out, first_bad, index_base, stream, opts(P));
+    return launch_generic<T, N>(linear_kernel<T, N, RECT, WL, 1, int>, g, obs, n, out, first_bad, index_base, stream, opts(1));
 }
 
 template <class T, int N, bool RECT>
 cudaError_t launch_linear_n(const DeviceGrid& g, const T* const* obs, size_t n, T* out, unsigned long long* first_bad,
                             unsigned long long index_base, cudaStream_t stream) {
     constexpr bool kCanWin = N <= kMaxWindowDimsLinear;
-    const bool has_win = kCanWin && g.win != nullptr && g.win_width == 2;
-    if constexpr (N >= 2) {  // grids beyond L2: bin-swept evaluation (sweep.cuh), from the window layout when there is one
+    // Window copy (capi.cu window_width): row pairs (N = 1, and small grids whose 2-fold copy still fits L1), else 2x2
+    // patches of the last two dimensions.
+    constexpr int kPatch = N >= 2 ? 4 : 2;
+    const bool has_patch = kCanWin && g.win != nullptr && g.win_width == kPatch;
+    const bool has_rows = N >= 2 && N <= 4 && g.win != nullptr && g.win_width == 2;
+    if constexpr (N >= 2) {  // grids beyond L2: bin-swept evaluation (sweep.cuh), from the patch layout when there is one
         bool swept = false;
         cudaError_t e = launch_sweep<T, N, RECT>(
-            g, 2, has_win ? 2 : 1, 1 << (N - 1), obs, n, out, first_bad, index_base, stream,
+            g, 2, has_patch ? kPatch : 1, has_patch ? 1 << (N - 2) : 1 << (N - 1), obs, n, out, first_bad, index_base, stream,
             [&](const T* const* sobs, size_t cnt, T* res, const unsigned* orig, unsigned long long base, unsigned long long* work) {
                 if constexpr (kCanWin) {
-                    if (has_win) return launch_linear_direct<T, N, RECT, true>(g, sobs, cnt, res, first_bad, base, stream, orig, work);
+                    if (has_patch) return launch_linear_direct<T, N, RECT, kPatch>(g, sobs, cnt, res, first_bad, base, stream, orig, work);
                 }
-                return launch_linear_direct<T, N, RECT, false>(g, sobs, cnt, res, first_bad, base, stream, orig, work);
+                return launch_linear_direct<T, N, RECT, 0>(g, sobs, cnt, res, first_bad, base, stream, orig, work);
             },
             swept);
         if (e != cudaSuccess || swept) return e;
     }
-    // Direct kernels gather from the window layout only while it is L2-resident.
+    // Direct kernels gather from a window copy only while it is L2-resident.
     if constexpr (kCanWin) {
-        if (has_win && g.nvals * sizeof(T) * 2 <= kWindowL2Bytes)
-            return launch_linear_direct<T, N, RECT, true>(g, obs, n, out, first_bad, index_base, stream, nullptr, nullptr);
+        if (has_patch && g.nvals * sizeof(T) * kPatch <= kWindowL2Bytes)
+            return launch_linear_direct<T, N, RECT, kPatch>(g, obs, n, out, first_bad, index_base, stream, nullptr, nullptr);
     }
-    return launch_linear_direct<T, N, RECT, false>(g, obs, n, out, first_bad, index_base, stream, nullptr, nullptr);
+    if constexpr (N >= 2 && N <= 4) {
+        if (has_rows) return launch_linear_direct<T, N, RECT, 2>(g, obs, n, out, first_bad, index_base, stream, nullptr, nullptr);
+    }
+    return launch_linear_direct<T, N, RECT, 0>(g, obs, n, out, first_bad, index_base, stream, nullptr, nullptr);
 }
 
 template <class T>

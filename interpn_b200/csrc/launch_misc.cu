@@ -43,9 +43,33 @@ __global__ void __launch_bounds__(kBlock) build_xwindow_kernel(const T* __restri
     }
 }
 
+// Patch layout (kernels.cuh linear_patches): pwin[f*4 + 2*i + j] = vals[f + i*Db + j], with i and j dropped to 0 where
+// the patch would leave the grid (never read: a footprint origin is at most dim-2).
+template <class T>
+__global__ void __launch_bounds__(kBlock) build_pwindow_kernel(const T* __restrict__ vals, T* __restrict__ pwin,
+                                                               unsigned long long nvals, unsigned long long da,
+                                                               unsigned long long db) {
+    const unsigned long long total = nvals * 4;
+    const unsigned long long gstride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+    for (unsigned long long k = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; k < total;
+         k += gstride) {
+        const unsigned long long f = k >> 2, i = (k >> 1) & 1, j = k & 1;
+        const unsigned long long ib = f % db, ia = (f / db) % da;
+        const unsigned long long ii = ia + i < da ? i : 0, jj = ib + j < db ? j : 0;
+        pwin[k] = vals[f + ii * db + jj];
+    }
+}
+
 cudaError_t launch_build_window(const DeviceGrid& g, cudaStream_t stream) {
     if (!g.win || g.nvals == 0) return cudaSuccess;
     const unsigned grid_dim = grid_for(g.nvals * g.win_width, g.sm_count, 8);
+    if (g.win_cross && g.method == 0) {  // INTERPN_B200_LINEAR
+        const unsigned long long da = g.dim[g.ndims - 2], db = g.dim[g.ndims - 1];
+        if (g.elem == 8) build_pwindow_kernel<double><<<grid_dim, kBlock, 0, stream>>>(static_cast<const double*>(g.vals), static_cast<double*>(g.win), g.nvals, da, db);
+        else build_pwindow_kernel<float><<<grid_dim, kBlock, 0, stream>>>(static_cast<const float*>(g.vals), static_cast<float*>(g.win), g.nvals, da, db);
+        count_launch();
+        return cudaGetLastError();
+    }
     if (g.win_cross) {
         const unsigned long long da = g.dim[g.ndims - 2], db = g.dim[g.ndims - 1];
         if (g.elem == 8) build_xwindow_kernel<double><<<grid_dim, kBlock, 0, stream>>>(static_cast<const double*>(g.vals), static_cast<double*>(g.win), g.nvals, da, db);

@@ -131,18 +131,83 @@ __device__ __forceinline__ T cubic_step_perm(T u0, T u1, T u2, T u3, const QuadD
 // (interior: as written; high end: the same expression on (v1,v2,v3); low end: -(wa*((v2-v1)/q) + wc*(v1-v0)) equals
 // wc*(u2-u1) + wa*((u1-u0)/q) on (v2,v1,v0) because negation commutes with every rounding — hence the exchanged
 // weights), and k1 is the interior slope wa1*((u3-u2)/div1) + wc1*(u2-u1) or the end slope 2*dy - k0.
+// The two quotients q0 = (u1-u0)/div0 and q1 = (u3-u2)/div1 are passed in (cubic_steps_rect).
 template <class T>
-__device__ __forceinline__ T cubic_step_perm(T u0, T u1, T u2, T u3, const QuadDim<T, true>& c, int fl, bool all_none) {
+__device__ __forceinline__ T cubic_step_tail(T u1, T u2, T dy, T q0, T q1, const QuadDim<T, true>& c, int fl, bool all_none) {
     using O = Ops<T>;
-    const bool fast = (fl & 8) != 0;
-    const T d10 = O::sub(u1, u0), dy = O::sub(u2, u1), d32 = O::sub(u3, u2);
-    const T k0 = O::add(O::mul(c.wa, dy), O::mul(c.wc, exact_div(d10, c.div0, c.rdiv0, fast)));
-    const T kint = O::add(O::mul(c.wa1, exact_div(d32, c.div1, c.rdiv1, fast)), O::mul(c.wc1, dy));
+    const T k0 = O::add(O::mul(c.wa, dy), O::mul(c.wc, q0));
+    const T kint = O::add(O::mul(c.wa1, q1), O::mul(c.wc1, dy));
     if (all_none) return hermite_fused(c.tt, u1, dy, k0, kint);
     const T k1 = (fl & 3) ? O::fma(T(2), dy, -k0) : kint;
     const T cub = hermite_fused(c.tt, u1, dy, k0, k1);
     const T linv = O::add(u2, O::mul(k1, O::sub(c.tt, T(1))));
     return (fl & 4) ? linv : cub;
+}
+
+// |v| in [2^-300, 2^301): exact_div's operand range, tested on the high word (three integer instructions).
+__device__ __forceinline__ bool exact_div_operand_ok(double v) {
+    return (static_cast<unsigned>(__double2hiint(v)) & 0x7fffffffu) - (723u << 20) < (601u << 20);
+}
+
+// M independent 1-D steps of one dimension (same parameters, inputs u[k][j]). f64: all 2M quotients take the
+// five-instruction sequence of device_math.cuh exact_div unconditionally, their operand guards are accumulated into
+// ONE predicate, and only a lane with an operand outside the guarded range redoes its quotients with the IEEE
+// division — one branch per group instead of one per quotient (ncu: the per-quotient guards and their
+// BSSY/BRA/BSYNC were a quarter of the instructions of the rectilinear kernel).
+template <int M, class T>
+__device__ __forceinline__ void cubic_steps_rect(const T (&u)[4][M], const QuadDim<T, true>& c, int fl, bool all_none,
+                                                 T (&out)[M]) {
+    using O = Ops<T>;
+    T d10[M], dy[M], d32[M], q0[M], q1[M];
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+        d10[j] = O::sub(u[1][j], u[0][j]);
+        dy[j] = O::sub(u[2][j], u[1][j]);
+        d32[j] = O::sub(u[3][j], u[2][j]);
+    }
+    if constexpr (sizeof(T) == 8) {
+        bool ok = (fl & 8) != 0;
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+            q0[j] = markstein_div_raw(d10[j], c.div0, c.rdiv0);
+            q1[j] = markstein_div_raw(d32[j], c.div1, c.rdiv1);
+            ok = ok && exact_div_operand_ok(d10[j]) && exact_div_operand_ok(d32[j]);
+        }
+        if (!ok) {
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                q0[j] = exact_div_slow(d10[j], c.div0);
+                q1[j] = exact_div_slow(d32[j], c.div1);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+            q0[j] = O::div(d10[j], c.div0);
+            q1[j] = O::div(d32[j], c.div1);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < M; ++j) out[j] = cubic_step_tail(u[1][j], u[2][j], dy[j], q0[j], q1[j], c, fl, all_none);
+}
+
+template <class T>
+__device__ __forceinline__ T cubic_step_perm(T u0, T u1, T u2, T u3, const QuadDim<T, true>& c, int fl, bool all_none) {
+    const T u[4][1] = {{u0}, {u1}, {u2}, {u3}};
+    T out[1];
+    cubic_steps_rect<1, T>(u, c, fl, all_none, out);
+    return out[0];
+}
+
+// Four steps on the rows of a sub-block (regular grids: four independent calls; the compiler interleaves them).
+template <class T>
+__device__ __forceinline__ void cubic_steps4(const T (&sub)[4][4], const QuadDim<T, false>& c, int fl, bool all_none, T (&out)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = cubic_step_perm(sub[0][j], sub[1][j], sub[2][j], sub[3][j], c, fl, all_none);
+}
+template <class T>
+__device__ __forceinline__ void cubic_steps4(const T (&sub)[4][4], const QuadDim<T, true>& c, int fl, bool all_none, T (&out)[4]) {
+    cubic_steps_rect<4, T>(sub, c, fl, all_none, out);
 }
 
 // The same step on inputs in natural order: the permutation is done with selects (dimension N-2, whose four inputs
@@ -269,13 +334,8 @@ __device__ __forceinline__ void quad4_rows(const EvalArgs<T, N>& a, const T* __r
                 quad4_rows<D - 1, T, N, RECT>(a, axes, idx + cubic_perm_k(mode, k) * stride, sp, flags, none_mask, sub[k]);
         }
         const QuadDim<T, RECT> c = quad4_dim<T, N>(a, axes, sp, D - 1);
-        if (all_none) {  // one warp-uniform branch around the four independent steps: they interleave
-#pragma unroll
-            for (int j = 0; j < 4; ++j) out[j] = cubic_step_perm(sub[0][j], sub[1][j], sub[2][j], sub[3][j], c, fl, true);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) out[j] = cubic_step_perm(sub[0][j], sub[1][j], sub[2][j], sub[3][j], c, fl, false);
-        }
+        if (all_none) cubic_steps4(sub, c, fl, true, out);  // one warp-uniform branch around the four independent steps
+        else cubic_steps4(sub, c, fl, false, out);
     }
 }
 

@@ -176,6 +176,16 @@ __device__ __forceinline__ bool markstein_operand_ok(double a) {
     return (e - 723u <= 600u) || ((hi << 1 | static_cast<unsigned>(__double2loint(a))) == 0u);
 }
 
+// The bare sequence (no sign fix-up for a zero numerator, no guard): callers test the operands themselves.
+__device__ __forceinline__ double markstein_div_raw(double a, double b, double rb) {
+    const double q0 = __dmul_rn(a, rb);
+    const double e0 = __fma_rn(-q0, b, a);
+    const double q1 = __fma_rn(e0, rb, q0);
+    const double e1 = __fma_rn(-q1, b, a);
+    return __fma_rn(e1, rb, q1);
+}
+__device__ __forceinline__ float markstein_div_raw(float a, float b, float) { return __fdiv_rn(a, b); }
+
 __device__ __forceinline__ double markstein_div(double a, double b, double rb) {
     const double q0 = __dmul_rn(a, rb);
     const double e0 = __fma_rn(-q0, b, a);

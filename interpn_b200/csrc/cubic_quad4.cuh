@@ -75,6 +75,18 @@ __device__ __forceinline__ QuadDim<T, true> quad4_dim(const EvalArgs<T, N>& a, c
     return c;
 }
 
+// v, or -0 when `cond` and v is a zero. The permuted low-end formulas produce v0-v2 (resp. a sum of sign-flipped
+// terms) where the reference produces -(v2-v0) (resp. minus the sum): equal bit for bit except that a zero comes out
+// as +0 instead of the reference's -0. Integer test and select, general (end-cell) path only.
+__device__ __forceinline__ double neg_zero_if(double v, bool cond) {
+    // one DSETP + one SEL on the high word (the low word of a zero is already 0)
+    const int hi = (cond && v == 0.0) ? static_cast<int>(0x80000000u) : __double2hiint(v);
+    return __hiloint2double(hi, __double2loint(v));
+}
+__device__ __forceinline__ float neg_zero_if(float v, bool cond) {
+    return (cond && (__float_as_int(v) << 1) == 0) ? __int_as_float(static_cast<int>(0x80000000u)) : v;
+}
+
 template <class T>
 __device__ __forceinline__ T hermite_fused(T t, T y0, T dy, T k0, T k1) {  // device_math.cuh hermite with c2 fused
     using O = Ops<T>;
@@ -102,10 +114,10 @@ __device__ __forceinline__ T cubic_step_perm(T u0, T u1, T u2, T u3, const QuadD
     using O = Ops<T>;
     const T half = T(0.5), two = T(2);
     const T tt = c.tt;
-    const T d20 = O::sub(u2, u0);
     const T dy = O::sub(u2, u1);
-    const T a = O::fma(half, d20, -dy);
     if (all_none) {
+        const T d20 = O::sub(u2, u0);
+        const T a = O::fma(half, d20, -dy);
         const T d31 = O::sub(u3, u1);
         const T b = O::fma(-half, d31, dy);
         const T c1 = O::add(dy, a);
@@ -113,6 +125,8 @@ __device__ __forceinline__ T cubic_step_perm(T u0, T u1, T u2, T u3, const QuadD
         const T c3 = O::sub(a, b);
         return O::add(u1, O::mul(tt, O::add(c1, O::mul(tt, O::add(c2, O::mul(tt, c3))))));
     }
+    const T d20 = neg_zero_if(O::sub(u2, u0), (fl & 3) == kModeLow);  // low end: the reference's -(v2 - v0)
+    const T a = O::fma(half, d20, -dy);
     const T k0 = O::mul(d20, half);
     const T knat = O::fma(two, dy, -k0);
     const T kint = O::mul(O::sub(u3, u1), half);
@@ -135,9 +149,10 @@ __device__ __forceinline__ T cubic_step_perm(T u0, T u1, T u2, T u3, const QuadD
 template <class T>
 __device__ __forceinline__ T cubic_step_tail(T u1, T u2, T dy, T q0, T q1, const QuadDim<T, true>& c, int fl, bool all_none) {
     using O = Ops<T>;
-    const T k0 = O::add(O::mul(c.wa, dy), O::mul(c.wc, q0));
+    const T k0s = O::add(O::mul(c.wa, dy), O::mul(c.wc, q0));
     const T kint = O::add(O::mul(c.wa1, q1), O::mul(c.wc1, dy));
-    if (all_none) return hermite_fused(c.tt, u1, dy, k0, kint);
+    if (all_none) return hermite_fused(c.tt, u1, dy, k0s, kint);
+    const T k0 = neg_zero_if(k0s, (fl & 3) == kModeLow);  // low end: the reference negates the sum
     const T k1 = (fl & 3) ? O::fma(T(2), dy, -k0) : kint;
     const T cub = hermite_fused(c.tt, u1, dy, k0, k1);
     const T linv = O::add(u2, O::mul(k1, O::sub(c.tt, T(1))));

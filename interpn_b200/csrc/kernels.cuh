@@ -662,7 +662,7 @@ __device__ __forceinline__ T cubic_rect_step(T v0, T v1, T v2, T v3, const Cubic
     const T k0 = low ? -k0r : k0r;
     const T y0 = high ? v2 : v1;
     const T y1 = low ? v0 : (high ? v3 : v2);
-    const T dy = none ? d21 : (low ? -d10 : d32);  // v0 - v1 == -(v1 - v0) exactly
+    const T dy = none ? d21 : (low ? O::sub(v0, v1) : d32);  // not -d10: equal neighbours must give +0, like the reference
     T k1 = O::sub(O::mul(two, dy), k0);
     if (none) k1 = O::add(O::mul(c.wa1, exact_div(d32, c.div1, c.rdiv1, c.fast)), O::mul(c.wc1, d21));
     const T cub = hermite(c.tt, y0, dy, k0, k1);

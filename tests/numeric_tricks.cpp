@@ -1,6 +1,6 @@
-// numeric_tricks.cpp — CPU re-check of the three division-avoiding sequences of
-// interpn_b200/csrc/device_math.cuh (markstein_div / exact_div, fast_cell, nearest_upper) against
-// the IEEE operations the reference performs. Test infrastructure: compiled and run by
+// numeric_tricks.cpp — CPU re-check of the division-avoiding sequences of interpn_b200/csrc/device_math.cuh
+// (markstein_div / exact_div, fast_cell, nearest_upper) and of the exact fusions, permuted end-cell formulas and
+// merged operand guard of cubic_quad4.cuh against the IEEE operations the reference performs. Test infrastructure: compiled and run by
 // tests/test_numeric_tricks.py with g++ -O2 -ffp-contract=off (std::fma is a single rounding).
 //
 // Usage: numeric_tricks <millions of random trials>; prints "OK <trials>" or the first counterexample.
@@ -115,6 +115,61 @@ int main(int argc, char** argv) {
         if (operand_ok(a)) {
             const double w = a / b, g = markstein_div(a, b, 1.0 / b);
             if (bits(w) != bits(g)) FAIL("markstein_div: a=%a b=%a got=%a want=%a", a, b, g, w);
+        }
+    }
+    // ---- cubic_quad4.cuh: unclamped cell proof, exact fusions, permuted end-cell formulas, merged operand guard ----
+    for (long it = 0; it < trials / 4; ++it) {
+        const double step = std::ldexp(0.5 + u01(), (int)(rnd() % 61) - 30);
+        const double rstep = 1.0 / step, lim = step * (1.0 - 0x1p-20);
+        const double start = (u01() - 0.5) * std::ldexp(1.0, (int)(rnd() % 40) - 10);
+        const int dim = 4 + (int)(rnd() % 300);
+        const int k = (int)(rnd() % (unsigned)dim);
+        double x;
+        switch (rnd() % 4) {
+            case 0: x = start + step * (double)k; break;
+            case 1: x = nudge(start + step * (double)k, (int)(rnd() % 9) - 4); break;
+            default: x = start + step * (double)(dim - 1) * (2.0 * u01() - 0.5); break;
+        }
+        // quad4_locate: f~ = floor(d*rstep) proven by 0 <= fma(-f~, step, d) <= lim, |f~| <= 2^30
+        const double d = x - start;
+        const int f = floor_sat(d * rstep);
+        const double r = std::fma(-(double)f, step, d);
+        if (r >= 0.0 && r <= lim && (unsigned)f + (1u << 30) <= (1u << 31)) {
+            const double q = std::floor(d / step);
+            if (q != (double)f) FAIL("cubic cell: x=%a start=%a step=%a f=%d ref=%a", x, start, step, f, q);
+        }
+        // grid values over a wide (normal) range, sometimes equal neighbours
+        const int ex = (int)(rnd() % 600) - 300;
+        double v[4];
+        for (double& w : v) w = std::ldexp(u01() - 0.5, ex + (int)(rnd() % 8));
+        if (rnd() % 16 == 0) v[1] = v[0];
+        if (rnd() % 16 == 0) v[2] = v[1];
+        const double dy = v[2] - v[1], d20 = v[2] - v[0], d31 = v[3] - v[1];
+        const double k0 = d20 * 0.5, k1 = d31 * 0.5;
+        const double a_ref = k0 - dy, b_ref = -k1 + dy;
+        const double a_f = std::fma(0.5, d20, -dy), b_f = std::fma(-0.5, d31, dy);
+        if (bits(a_ref) != bits(a_f) || bits(b_ref) != bits(b_f)) FAIL("fused a/b: v=%a %a %a %a", v[0], v[1], v[2], v[3]);
+        if (bits(b_ref - (a_ref + a_ref)) != bits(std::fma(-2.0, a_ref, b_ref))) FAIL("fused c2: a=%a b=%a", a_ref, b_ref);
+        const double two = 2.0;
+        if (bits(two * dy - k0) != bits(std::fma(2.0, dy, -k0))) FAIL("fused k1: dy=%a k0=%a", dy, k0);
+        // regular low end (multicubic/regular.rs:519-530) on permuted inputs (v2,v1,v0): k0 = -(v2-v0)/2, dy = v0-v1
+        // (a zero comes out as +0 where the reference has -0: neg_zero_if)
+        auto neg_zero = [](double w) { return w == 0.0 ? -0.0 : w; };
+        if (bits(-(v[2] - v[0]) / two) != bits(neg_zero(v[0] - v[2]) * 0.5)) FAIL("low-end k0");
+        // rectilinear low end (multicubic/rectilinear.rs:463-477): -(a*((v2-v1)/q) + c*(v1-v0)) with the weights
+        // exchanged on the permuted inputs u = (v2,v1,v0): c*(u2-u1) + a*((u1-u0)/q)
+        const double qq = 0.25 + 4.0 * u01(), wa = 1.0 / (1.0 + qq), wc = qq / (qq + 1.0);
+        const double low_ref = -(wa * ((v[2] - v[1]) / qq) + wc * (v[1] - v[0]));
+        const double u0 = v[2], u1 = v[1], u2 = v[0];
+        const double low_perm = neg_zero(wc * (u2 - u1) + wa * ((u1 - u0) / qq));
+        if (bits(low_ref) != bits(low_perm)) FAIL("rect low end: v=%a %a %a q=%a", v[0], v[1], v[2], qq);
+        // merged guard (exact_div_operand_ok on the high word) + bare sequence == IEEE division
+        const double num = (rnd() % 8 == 0) ? nudge(qq * (double)(rnd() % 1000), (int)(rnd() % 5) - 2) : v[1] - v[0];
+        const unsigned hi = (unsigned)(bits(num) >> 32);
+        if ((hi & 0x7fffffffu) - (723u << 20) < (601u << 20)) {
+            const double rq = 1.0 / qq;
+            const double q0 = num * rq, e0 = std::fma(-q0, qq, num), q1 = std::fma(e0, rq, q0), e1 = std::fma(-q1, qq, num);
+            if (bits(std::fma(e1, rq, q1)) != bits(num / qq)) FAIL("bare sequence: a=%a b=%a", num, qq);
         }
     }
     // exhaustive neighbourhood of the tie for a few steps: e = step/2 + k ulps, k = -64..64

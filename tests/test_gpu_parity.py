@@ -177,7 +177,42 @@ def test_cubic_four_node_axes(ib, oracle, dtype):
         assert_same_bits(out, oracle.interpn_rectilinear("cubic", grids, vals, obs, linearize_extrapolation=lin))
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("ndims", [1, 2, 3, 4])
+@pytest.mark.parametrize("method", ["linear", "cubic"])
+def test_plateau_grids_keep_the_sign_of_zero(ib, oracle, method, ndims, dtype):
+    """Grid values drawn from {-1, -0.0, 0, 1}: neighbouring values are often equal and many results are exactly
+    zero. The permuted end-cell formulas of the four-points-per-quad cubic kernels (cubic_quad4.cuh) evaluate v0-v2
+    where the reference evaluates -(v2-v0); the two differ in the sign of a zero, which neg_zero_if restores — so the
+    comparison stays bit for bit, including -0 against +0."""
+    rng = np.random.default_rng(77 + ndims)
+    n = 40000
+    dims, grids, starts, steps, vals, obs = random_case(rng, ndims, n, 4, {1: 30, 2: 12, 3: 8, 4: 6}[ndims], dtype)
+    vals = rng.choice(np.array([-1.0, -0.0, 0.0, 1.0]), size=vals.size, p=[0.2, 0.2, 0.4, 0.2]).astype(dtype)
+    sfx = "f64" if dtype == np.float64 else "f32"
+    for linearize in ((False, True) if method == "cubic" else (True,)):
+        extra = (linearize,) if method == "cubic" else ()
+        out = np.full(n, 7.0, dtype=dtype)
+        getattr(ib.raw, f"interpn_{method}_regular_{sfx}")(dims, starts, steps, vals, *extra, obs, out)
+        want = oracle.interpn_regular(method, dims, starts, steps, vals, obs, linearize_extrapolation=linearize, nthreads=4)
+        if ndims <= 2:
+            assert (want == 0).sum() > n // 100  # the case is exercised
+        assert_same_bits(out, want, f"plateau {method} regular N={ndims} {sfx} lin={linearize}")
+        out = np.full(n, 7.0, dtype=dtype)
+        getattr(ib.raw, f"interpn_{method}_rectilinear_{sfx}")(grids, vals, *extra, obs, out)
+        want = oracle.interpn_rectilinear(method, grids, vals, obs, linearize_extrapolation=linearize, nthreads=4)
+        assert_same_bits(out, want, f"plateau {method} rectilinear N={ndims} {sfx} lin={linearize}")
+
+
 WORKLOADS = [
+    ("x_linear3d_reg100", np.float64, 200_000),
+    ("x_linear4d_reg32", np.float64, 200_000),
+    ("x_linear4d_rect32", np.float64, 200_000),
+    ("x_cubic4d_reg32", np.float64, 100_000),
+    ("x_cubic3d_rect100", np.float64, 200_000),
+    ("x_cubic4d_rect32", np.float64, 60_000),
+    ("x_cubic4d_reg32", np.float32, 100_000),
+    ("x_cubic3d_rect100", np.float32, 200_000),
     ("c1_linear3d_reg20", np.float64, 200_000),
     ("c2_cubic3d_reg100", np.float64, 200_000),
     ("c3_linear4d_rect64", np.float64, 200_000),

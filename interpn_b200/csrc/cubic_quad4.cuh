@@ -246,7 +246,31 @@ __device__ __forceinline__ void cubic_perm(int mode, int (&k)[4]) {
     k[3] = 3;
 }
 
-// Cell location of one point on every dimension, regular grid (ref: multicubic/regular.rs:432-469 and :356-360).
+// The exact twin of the fast location below for the rare coordinate it cannot prove (within 2^-20 of a node from
+// below, beyond 2^30 cells, NaN/inf, a numerator outside exact_div's range): IEEE divisions, out of line.
+template <class T>
+struct Quad4Exact {
+    T t;
+    int f;
+    int ok;
+};
+template <class T>
+static __device__ __noinline__ Quad4Exact<T> quad4_locate_exact(T x, T start, T step, T rstep, bool fast_div, int dim) {
+    using O = Ops<T>;
+    Quad4Exact<T> r;
+    r.ok = floor_cell(x, start, step, rstep, fast_div, r.f);
+    const int origin = min(max(r.f, 1) - 1, dim - 4);
+    const T x1 = O::add(start, O::mul(step, O::from_int(origin + 1)));
+    r.t = O::div(O::sub(x, x1), step);
+    return r;
+}
+
+// Cell location of one point on every dimension, regular grid (ref: multicubic/regular.rs:432-469 and :356-360):
+// f = floor((x - start)/step) (the reference's iloc + 1), footprint origin clamp(f - 1, 0, dim - 4), saturation class
+// from f, and t = (x - x1)/step relative to footprint node 1 (x1 = start + step*(origin + 1), never fused).
+// f64: f~ = floor(RN(d * RN(1/step))) is proven by the FMA remainder 0 <= d - f~*step <= step*(1 - 2^-20)
+// (device_math.cuh fast_cell; the unclamped f is needed here, so the remainder is taken against f~ itself) and t takes
+// the Markstein sequence; one accumulated predicate sends the rare unproven coordinate to quad4_locate_exact.
 template <class T, int N>
 __device__ __forceinline__ bool quad4_locate(const EvalArgs<T, N>& a, const T*, const T (&x)[N], QuadSlot<T, N, false>& s) {
     using O = Ops<T>;
@@ -254,29 +278,32 @@ __device__ __forceinline__ bool quad4_locate(const EvalArgs<T, N>& a, const T*, 
     int base = 0, flags = 0;
 #pragma unroll
     for (int d = 0; d < N; ++d) {
+        const int dim = a.dim[d];
         int f = 0;
-        bool proven = false;
+        T t = T(0);
+        bool good = false;
         if constexpr (sizeof(T) == 8) {
-            // f~ = floor(RN(d * RN(1/step))) with the FMA remainder as proof (device_math.cuh fast_cell; here the
-            // unclamped f is needed, so the remainder is always taken against f~ itself).
             const double dd = __dsub_rn(x[d], a.start[d]);
             f = __double2int_rd(__dmul_rn(dd, a.rstep[d]));
             const double r = __fma_rn(-__int2double_rn(f), a.step[d], dd);
-            proven = a.fast_div != 0 && r >= 0.0 && r <= a.lim[d] && static_cast<unsigned>(f) + (1u << 30) <= (1u << 31);
+            const int origin = min(max(f, 1) - 1, dim - 4);
+            const double x1 = __dadd_rn(a.start[d], __dmul_rn(a.step[d], __int2double_rn(origin + 1)));
+            const double e = __dsub_rn(x[d], x1);
+            t = markstein_div(e, a.step[d], a.rstep[d]);
+            good = a.fast_div != 0 && r >= 0.0 && r <= a.lim[d] && static_cast<unsigned>(f) + (1u << 30) <= (1u << 31) &&
+                   markstein_operand_ok(e);
         }
-        if (!proven) ok = floor_cell(x[d], a.start[d], a.step[d], a.rstep[d], a.fast_div != 0, f) && ok;
-        const int dim = a.dim[d];
+        if (!good) {
+            const Quad4Exact<T> ex = quad4_locate_exact<T>(x[d], a.start[d], a.step[d], a.rstep[d], a.fast_div != 0, dim);
+            f = ex.f;
+            t = ex.t;
+            ok = ex.ok && ok;
+        }
         const int origin = min(max(f, 1) - 1, dim - 4);
-        int mode;
-        bool outside;
-        if (f < 0) { mode = kModeLow; outside = true; }
-        else if (f == 0) { mode = kModeLow; outside = false; }
-        else if (f > dim - 2) { mode = kModeHigh; outside = true; }
-        else if (f == dim - 2) { mode = kModeHigh; outside = false; }
-        else { mode = kModeNone; outside = false; }
-        const T x1 = O::add(a.start[d], O::mul(a.step[d], O::from_int(origin + 1)));
-        const T t = exact_div(O::sub(x[d], x1), a.step[d], a.rstep[d], a.fast_div != 0);
-        s.tt[d] = mode == kModeNone ? t : (mode == kModeLow ? -t : O::sub(t, T(1)));
+        // tested in the reference's order: f < 0 OutsideLow, f == 0 InsideLow, f > dim-2 OutsideHigh, f == dim-2 InsideHigh
+        const bool low = f <= 0, high = f >= dim - 2, outside = f < 0 || f > dim - 2;
+        const int mode = low ? kModeLow : (high ? kModeHigh : kModeNone);
+        s.tt[d] = low ? -t : (high ? O::sub(t, T(1)) : t);
         base += origin * a.istride[d];
         flags |= (mode | ((outside && a.linearize) ? 4 : 0)) << (4 * d);
     }

@@ -51,6 +51,9 @@ def parse_args():
     ap.add_argument("--points", type=int, default=0, help="query points per GPU (default: the workload's full size, capped at 1e8)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU baseline sample")
+    ap.add_argument("--arithmetic", default=os.environ.get("INTERPN_B200_ARITHMETIC", "strict"), choices=["strict", "fma"],
+                    help="reference build whose arithmetic is reproduced: crate default features (strict, the headline) "
+                         "or the crate's `fma` feature = the Python wheel's build (libinterpn_b200_fma.so)")  # fmt: skip
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -120,7 +123,7 @@ def cpu_baseline(w, target_seconds: float, nthreads: int | None = None, steps: i
         "cores": cores,
         "kind": "port",
         "sample": f"first {n} query points of {w.name} (same grid, same generator), {len(times)} pass(es), "
-                  f"oracle port of interpn 0.8.2 (strict arithmetic, -O3 -march=x86-64-v3), std::thread x{cores}",
+                  f"oracle port of interpn 0.8.2 ({'fma' if oracle.DEFAULT_FMA else 'strict'} arithmetic, -O3 -march=x86-64-v3), std::thread x{cores}",
         "ms_per_pass": dt * 1e3,
     }
     return n / dt, info, dt
@@ -420,6 +423,7 @@ def run_b200(args):
             "points_per_gpu": n,
             "out_of_bounds_fraction": w.oob_fraction,
             "linearize_extrapolation": bool(w.linearize),
+            "arithmetic": args.arithmetic,
             "l2": f"query arrays ({n * (w.ndims + 1) * 8 / 1e9:.2f} GB per step) exceed L2; the {w.nvals * 8 / 1e6:.0f} MB grid is reused across steps by design",
             "parallelism": f"query batch sharded over {world} GPU(s), grid replicated by one NCCL broadcast" if distributed else "single GPU",
         },
@@ -447,6 +451,9 @@ def run_b200(args):
 
 def main():
     args = parse_args()
+    # read by interpn_b200/_lib.py (which library is loaded) and by oracle/oracle.py (which arithmetic the
+    # parity spot check and the CPU legs run in) when they are first imported
+    os.environ["INTERPN_B200_ARITHMETIC"] = args.arithmetic
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)

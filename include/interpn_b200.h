@@ -92,6 +92,12 @@ int interpn_b200_set_device(int device);
 uint64_t interpn_b200_launch_count(void);
 /* How many of those launches were bin-swept evaluations (grids beyond L2, interpn_b200/csrc/sweep.cuh). */
 uint64_t interpn_b200_swept_launch_count(void);
+/* Arithmetic flavour this build of the library reproduces: 0 = the crate's default features (no fused
+ * multiply-add anywhere, e.g. multilinear/regular.rs:382-385), 1 = the crate's `fma` feature (mul_add at the
+ * reference's sites: multilinear/regular.rs:334-337,377-388, multicubic/mod.rs:84-90,111-116,
+ * multicubic/regular.rs:528-564, nearest/regular.rs:272-275, one_dim/linear.rs:30-35; the Python wheel's build,
+ * pyproject.toml:72). libinterpn_b200.so is flavour 0, libinterpn_b200_fma.so flavour 1; same symbols. */
+int interpn_b200_arithmetic(void);
 /* Streaming multiprocessors of the current device (148 on B200); 0 when there is no device. */
 int interpn_b200_sm_count(void);
 

@@ -11,8 +11,16 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
+# Arithmetic flavour (include/interpn_b200.h interpn_b200_arithmetic): "strict" reproduces the reference crate built
+# with default features, "fma" the crate's `fma` feature — the build of the reference's Python wheel
+# (pyproject.toml:72). Chosen once per process by INTERPN_B200_ARITHMETIC; each flavour is its own shared library.
+ARITHMETIC = os.environ.get("INTERPN_B200_ARITHMETIC", "strict").lower()
+if ARITHMETIC not in ("strict", "fma"):
+    raise ImportError(f"INTERPN_B200_ARITHMETIC must be 'strict' or 'fma', not {ARITHMETIC!r}")
 # INTERPN_B200_LIBRARY selects another build of the same library (kernel-tuning experiments only).
-LIB_PATH = os.environ.get("INTERPN_B200_LIBRARY") or os.path.join(_HERE, "libinterpn_b200.so")
+LIB_PATH = os.environ.get("INTERPN_B200_LIBRARY") or os.path.join(
+    _HERE, "libinterpn_b200_fma.so" if ARITHMETIC == "fma" else "libinterpn_b200.so"
+)
 
 # Status codes of include/interpn_b200.h
 OK = 0

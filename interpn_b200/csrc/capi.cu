@@ -797,6 +797,7 @@ int interpn_b200_set_device(int device) {
     return INTERPN_B200_OK;
 }
 
+int interpn_b200_arithmetic(void) { return IB200_ARITH_FMA; }
 uint64_t interpn_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 uint64_t interpn_b200_swept_launch_count(void) { return g_swept.load(std::memory_order_relaxed); }
 

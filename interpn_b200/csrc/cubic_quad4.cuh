@@ -95,7 +95,7 @@ __device__ __forceinline__ T hermite_fused(T t, T y0, T dy, T k0, T k1) {  // de
     const T c1 = O::add(dy, a);
     const T c2 = O::fma(T(-2), a, b);
     const T c3 = O::sub(a, b);
-    return O::add(y0, O::mul(t, O::add(c1, O::mul(t, O::add(c2, O::mul(t, c3))))));
+    return muladd(muladd(muladd(c3, t, c2), t, c1), t, y0);
 }
 
 // One 1-D cubic step on inputs that are already permuted for the saturation class:
@@ -123,7 +123,7 @@ __device__ __forceinline__ T cubic_step_perm(T u0, T u1, T u2, T u3, const QuadD
         const T c1 = O::add(dy, a);
         const T c2 = O::fma(-two, a, b);
         const T c3 = O::sub(a, b);
-        return O::add(u1, O::mul(tt, O::add(c1, O::mul(tt, O::add(c2, O::mul(tt, c3))))));
+        return muladd(muladd(muladd(c3, tt, c2), tt, c1), tt, u1);
     }
     const T d20 = neg_zero_if(O::sub(u2, u0), (fl & 3) == kModeLow);  // low end: the reference's -(v2 - v0)
     const T a = O::fma(half, d20, -dy);
@@ -135,8 +135,8 @@ __device__ __forceinline__ T cubic_step_perm(T u0, T u1, T u2, T u3, const QuadD
     const T c1 = O::add(dy, a);
     const T c2 = O::fma(-two, a, b);
     const T c3 = O::sub(a, b);
-    const T cub = O::add(u1, O::mul(tt, O::add(c1, O::mul(tt, O::add(c2, O::mul(tt, c3))))));
-    const T linv = O::add(u2, O::mul(k1, O::sub(tt, T(1))));
+    const T cub = muladd(muladd(muladd(c3, tt, c2), tt, c1), tt, u1);
+    const T linv = muladd(k1, O::sub(tt, T(1)), u2);  // fused under the fma feature (multicubic/regular.rs:553-564)
     return (fl & 4) ? linv : cub;
 }
 
@@ -149,13 +149,17 @@ __device__ __forceinline__ T cubic_step_perm(T u0, T u1, T u2, T u3, const QuadD
 template <class T>
 __device__ __forceinline__ T cubic_step_tail(T u1, T u2, T dy, T q0, T q1, const QuadDim<T, true>& c, int fl, bool all_none) {
     using O = Ops<T>;
-    const T k0s = O::add(O::mul(c.wa, dy), O::mul(c.wc, q0));
-    const T kint = O::add(O::mul(c.wa1, q1), O::mul(c.wc1, dy));
+    // centered_difference_nonuniform's a*b + c*d (cdn_sum). Under the fma feature the SECOND product is the rounded
+    // one, and in a low end cell the exchanged weights exchange the products' roles: the reference's
+    // -fma(a, (v2-v1)/q, c*(v1-v0)) is fma(wc, q0, wa*dy) on the permuted inputs.
+    T k0s = cdn_sum(c.wa, dy, c.wc, q0);
+    const T kint = cdn_sum(c.wa1, q1, c.wc1, dy);
     if (all_none) return hermite_fused(c.tt, u1, dy, k0s, kint);
+    if constexpr (kArithFma) k0s = (fl & 3) == kModeLow ? cdn_sum(c.wc, q0, c.wa, dy) : k0s;
     const T k0 = neg_zero_if(k0s, (fl & 3) == kModeLow);  // low end: the reference negates the sum
     const T k1 = (fl & 3) ? O::fma(T(2), dy, -k0) : kint;
     const T cub = hermite_fused(c.tt, u1, dy, k0, k1);
-    const T linv = O::add(u2, O::mul(k1, O::sub(c.tt, T(1))));
+    const T linv = O::add(u2, O::mul(k1, O::sub(c.tt, T(1))));  // not fused by the flattened structs (N <= 4)
     return (fl & 4) ? linv : cub;
 }
 

@@ -194,16 +194,42 @@ __device__ __forceinline__ double markstein_div(double a, double b, double rb) {
     return copysign(__fma_rn(e1, rb, q1), a);
 }
 
-// ref: multicubic/mod.rs:72-91 (strict arithmetic)
+// ---------------------------------------------------------------------------------------------
+// Arithmetic flavour. The reference has two builds: default features (every a*b+c is two rounded operations) and
+// the `fma` cargo feature (Cargo.toml; the Python wheel is built with it, pyproject.toml:72), which calls mul_add at a
+// fixed list of sites. The library is compiled once per flavour (csrc/Makefile: libinterpn_b200.so and
+// libinterpn_b200_fma.so, -DIB200_ARITH_FMA=1); muladd() is a*b+c the way the flavour's reference build computes it
+// at such a site. FUSE = false marks a site the reference leaves unfused even with the feature (the recursive twins'
+// x0, multilinear/regular_recursive.rs:310-313; the flattened rectilinear cubic's linearized extrapolation,
+// multicubic/rectilinear.rs:480-540).
+// ---------------------------------------------------------------------------------------------
+#ifndef IB200_ARITH_FMA
+#define IB200_ARITH_FMA 0
+#endif
+constexpr bool kArithFma = IB200_ARITH_FMA != 0;
+
+template <bool FUSE = true, class T>
+__device__ __forceinline__ T muladd(T a, T b, T c) {
+    if constexpr (kArithFma && FUSE) return Ops<T>::fma(a, b, c);
+    else return Ops<T>::add(Ops<T>::mul(a, b), c);
+}
+// centered_difference_nonuniform's a*b + c*d (ref: multicubic/mod.rs:111-116; fma feature: mul_add(a, b, c*d))
+template <class T>
+__device__ __forceinline__ T cdn_sum(T a, T b, T c, T d) {
+    return muladd(a, b, Ops<T>::mul(c, d));
+}
+
+// ref: multicubic/mod.rs:72-91. c2 = b - (a+a) is issued as fma(-2, a, b): a+a is exact, so the bits are the same
+// in both flavours. The polynomial is y0 + t*(c1 + t*(c2 + t*c3)), three chained mul_add under the fma feature.
 template <class T>
 __device__ __forceinline__ T hermite(T t, T y0, T dy, T k0, T k1) {
     using O = Ops<T>;
     T a = O::sub(k0, dy);
     T b = O::add(-k1, dy);
     T c1 = O::add(dy, a);
-    T c2 = O::sub(b, O::add(a, a));
+    T c2 = O::fma(T(-2), a, b);
     T c3 = O::sub(a, b);
-    return O::add(y0, O::mul(t, O::add(c1, O::mul(t, O::add(c2, O::mul(t, c3))))));
+    return muladd(muladd(muladd(c3, t, c2), t, c1), t, y0);
 }
 
 }  // namespace ib200

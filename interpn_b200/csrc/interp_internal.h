@@ -5,6 +5,11 @@
 #include <stddef.h>
 #include <stdint.h>
 
+// 1 in the build that reproduces the crate's `fma` feature (device_math.cuh kArithFma), else 0.
+#ifndef IB200_ARITH_FMA
+#define IB200_ARITH_FMA 0
+#endif
+
 namespace ib200 {
 
 constexpr int kMaxNd = 8;

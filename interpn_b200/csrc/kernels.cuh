@@ -204,7 +204,7 @@ __device__ __forceinline__ void linear_rows(const T* __restrict__ vals, const T*
         linear_rows<D - 1, T, N, WIN, I>(vals, win, idx, stride, t, lo);
         linear_rows<D - 1, T, N, WIN, I>(vals, win, idx + stride[D - 1], stride, t, hi);
 #pragma unroll
-        for (int j = 0; j < 2; ++j) out[j] = O::add(lo[j], O::mul(t[D - 1], O::sub(hi[j], lo[j])));
+        for (int j = 0; j < 2; ++j) out[j] = muladd(t[D - 1], O::sub(hi[j], lo[j]), lo[j]);
     }
 }
 
@@ -224,7 +224,7 @@ __device__ __forceinline__ void linear_patches(const T* __restrict__ win, I idx,
         linear_patches<D - 1, T, N, I>(win, idx, stride, t, lo);
         linear_patches<D - 1, T, N, I>(win, idx + stride[D - 1], stride, t, hi);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) out[j] = O::add(lo[j], O::mul(t[D - 1], O::sub(hi[j], lo[j])));
+        for (int j = 0; j < 4; ++j) out[j] = muladd(t[D - 1], O::sub(hi[j], lo[j]), lo[j]);
     }
 }
 
@@ -239,13 +239,13 @@ __device__ __forceinline__ T linear_tree(const T* __restrict__ vals, const T* __
         static_assert(N >= 2, "the patch layout needs two dimensions");
         T v[4];
         linear_patches<N - 2, T, N, I>(win, base, stride, t, v);
-        const T r0 = O::add(v[0], O::mul(t[N - 2], O::sub(v[2], v[0])));
-        const T r1 = O::add(v[1], O::mul(t[N - 2], O::sub(v[3], v[1])));
-        return O::add(r0, O::mul(t[N - 1], O::sub(r1, r0)));
+        const T r0 = muladd(t[N - 2], O::sub(v[2], v[0]), v[0]);
+        const T r1 = muladd(t[N - 2], O::sub(v[3], v[1]), v[1]);
+        return muladd(t[N - 1], O::sub(r1, r0), r0);
     } else {
         T r[2];
         linear_rows<N - 1, T, N, WIN, I>(vals, win, base, stride, t, r);
-        return O::add(r[0], O::mul(t[N - 1], O::sub(r[1], r[0])));
+        return muladd(t[N - 1], O::sub(r[1], r[0]), r[0]);
     }
 }
 
@@ -278,7 +278,8 @@ __device__ __forceinline__ bool linear_locate(const EvalArgs<T, N>& a, const T* 
             int iloc = 0;
             ok = floor_cell(x, a.start[d], a.step[d], a.rstep[d], a.fast_div != 0, iloc) && ok;
             origin = clamp_cell(iloc, a.dim[d] - 2);
-            T x0 = O::add(a.start[d], O::mul(a.step[d], O::from_int(origin)));
+            // x0: fused under the fma feature by the flattened structs (N <= 6), not by the recursive twins
+            T x0 = muladd<(N <= 6)>(a.step[d], O::from_int(origin), a.start[d]);
             t[d] = exact_div(O::sub(x, x0), a.step[d], a.rstep[d], a.fast_div != 0);
         }
         base += static_cast<I>(origin) * stride[d];
@@ -317,7 +318,7 @@ __device__ __forceinline__ bool nearest_locate(const EvalArgs<T, N>& a, const T*
             int iloc = 0;
             ok = floor_cell(x, a.start[d], a.step[d], a.rstep[d], a.fast_div != 0, iloc) && ok;
             origin = clamp_cell(iloc, a.dim[d] - 2);
-            T x0 = O::add(a.start[d], O::mul(a.step[d], O::from_int(origin)));
+            T x0 = muladd(a.step[d], O::from_int(origin), a.start[d]);
             dt = exact_div(O::sub(x, x0), a.step[d], a.rstep[d], a.fast_div != 0);
         }
         const int off = (dt <= half) ? 0 : 1;  // tie -> lower index; NaN (rectilinear only) -> upper
@@ -340,7 +341,7 @@ __device__ __forceinline__ bool linear_locate_fast(const EvalArgs<double, N>& a,
         int origin;
         double od, dd;
         sure = fast_cell(xs[d], a.start[d], a.step[d], a.rstep[d], a.lim[d], a.dim[d], origin, od, dd) && sure;
-        const double x0 = __dadd_rn(a.start[d], __dmul_rn(a.step[d], od));
+        const double x0 = muladd<(N <= 6)>(a.step[d], od, a.start[d]);
         const double e = __dsub_rn(xs[d], x0);
         sure = markstein_operand_ok(e) && sure;
         t[d] = markstein_div(e, a.step[d], a.rstep[d]);
@@ -359,7 +360,7 @@ __device__ __forceinline__ bool nearest_locate_fast(const EvalArgs<double, N>& a
         int origin;
         double od, dd;
         sure = fast_cell(xs[d], a.start[d], a.step[d], a.rstep[d], a.lim[d], a.dim[d], origin, od, dd) && sure;
-        const double x0 = __dadd_rn(a.start[d], __dmul_rn(a.step[d], od));
+        const double x0 = muladd(a.step[d], od, a.start[d]);
         const double e = __dsub_rn(xs[d], x0);
         const int off = nearest_upper(e, a.hstep[d], a.tau[d]) ? 1 : 0;
         idx += static_cast<I>(origin + off) * stride[d];
@@ -542,7 +543,7 @@ __device__ __forceinline__ T cubic_regular_step(T v0, T v1, T v2, T v3, const Cu
     const T knat = O::sub(O::mul(two, dy), k0);  // natural-spline end condition
     const T k1 = (low || high) ? knat : sb;
     const T cub = hermite(c.tt, y0, dy, k0, k1);
-    const T lin = O::add(y1, O::mul(k1, c.ttm1));
+    const T lin = muladd(k1, c.ttm1, y1);
     return c.lin ? lin : cub;
 }
 
@@ -642,15 +643,15 @@ __device__ __forceinline__ void cubic_rect_locate(T x, const T* __restrict__ g, 
 // (x / 1.0, exact) dropped (ref: multicubic/mod.rs:103-117, rectilinear.rs:449-450). Like the
 // regular-grid step this is select-based: the one data-dependent quotient of k0 picks its
 // numerator by case; k1's quotient exists only in the interior case.
-template <class T>
+template <bool RECURSIVE = false, class T>
 __device__ __forceinline__ T cubic_rect_step(T v0, T v1, T v2, T v3, const CubicRectDim<T>& c, bool all_none) {
     using O = Ops<T>;
     const T two = T(2);
     const T d10 = O::sub(v1, v0), d21 = O::sub(v2, v1), d32 = O::sub(v3, v2);
     if (all_none) {
         // k0: h01 = r, h12 = 1 -> b = (v2-v1)/1, d = (v1-v0)/r;  k1: h01 = 1, h12 = s -> b = (v3-v2)/s, d = (v2-v1)/1
-        T k0 = O::add(O::mul(c.wa, d21), O::mul(c.wc, exact_div(d10, c.div0, c.rdiv0, c.fast)));
-        T k1 = O::add(O::mul(c.wa1, exact_div(d32, c.div1, c.rdiv1, c.fast)), O::mul(c.wc1, d21));
+        T k0 = cdn_sum(c.wa, d21, c.wc, exact_div(d10, c.div0, c.rdiv0, c.fast));
+        T k1 = cdn_sum(c.wa1, exact_div(d32, c.div1, c.rdiv1, c.fast), c.wc1, d21);
         return hermite(c.tt, v1, d21, k0, k1);
     }
     const bool low = c.mode == kModeLow, high = c.mode == kModeHigh, none = !(low || high);
@@ -658,15 +659,15 @@ __device__ __forceinline__ T cubic_rect_step(T v0, T v1, T v2, T v3, const Cubic
     // None: wa*(v2-v1) + wc*((v1-v0)/r)   Low: -(wa*((v2-v1)/q) + wc*(v1-v0))   High: wa*(v3-v2) + wc*((v2-v1)/p)
     const T pa = none ? d21 : (low ? q0 : d32);
     const T pc = low ? d10 : q0;
-    const T k0r = O::add(O::mul(c.wa, pa), O::mul(c.wc, pc));
+    const T k0r = cdn_sum(c.wa, pa, c.wc, pc);
     const T k0 = low ? -k0r : k0r;
     const T y0 = high ? v2 : v1;
     const T y1 = low ? v0 : (high ? v3 : v2);
     const T dy = none ? d21 : (low ? O::sub(v0, v1) : d32);  // not -d10: equal neighbours must give +0, like the reference
     T k1 = O::sub(O::mul(two, dy), k0);
-    if (none) k1 = O::add(O::mul(c.wa1, exact_div(d32, c.div1, c.rdiv1, c.fast)), O::mul(c.wc1, d21));
+    if (none) k1 = cdn_sum(c.wa1, exact_div(d32, c.div1, c.rdiv1, c.fast), c.wc1, d21);
     const T cub = hermite(c.tt, y0, dy, k0, k1);
-    const T lin = O::add(y1, O::mul(k1, c.ttm1));
+    const T lin = muladd<RECURSIVE>(k1, c.ttm1, y1);  // fused by the recursive twin only (rectilinear_recursive.rs)
     return c.lin ? lin : cub;
 }
 
@@ -679,10 +680,11 @@ struct CubicDimOf<T, true> {
     using type = CubicRectDim<T>;
 };
 
-template <class T, bool RECT>
+// RECURSIVE: called from the looping tree of N >= 5, the reference's recursive structs (fma-flavour quirks).
+template <class T, bool RECT, bool RECURSIVE = false>
 __device__ __forceinline__ T cubic_step(T v0, T v1, T v2, T v3, const typename CubicDimOf<T, RECT>::type& c,
                                         bool all_none) {
-    if constexpr (RECT) return cubic_rect_step(v0, v1, v2, v3, c, all_none);
+    if constexpr (RECT) return cubic_rect_step<RECURSIVE>(v0, v1, v2, v3, c, all_none);
     else return cubic_regular_step(v0, v1, v2, v3, c, all_none);
 }
 
@@ -726,12 +728,12 @@ __device__ __noinline__ T cubic_tree_loop(const T* __restrict__ p, const long lo
             if (((i + 1) & (q - 1)) == 0) {
                 const unsigned slot = (((i + 1) >> (2 * j)) - 1) & 3u;
                 const T(&s)[4] = store[j - 1];
-                store[j][slot] = cubic_step<T, RECT>(s[0], s[1], s[2], s[3], c[j - 1], false);
+                store[j][slot] = cubic_step<T, RECT, true>(s[0], s[1], s[2], s[3], c[j - 1], false);
             }
         }
     }
     const T(&s)[4] = store[N - 1];
-    return cubic_step<T, RECT>(s[0], s[1], s[2], s[3], c[N - 1], false);
+    return cubic_step<T, RECT, true>(s[0], s[1], s[2], s[3], c[N - 1], false);
 }
 
 // One query point of the cubic evaluation. Must be called by all 32 lanes of a warp (the

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kBlock) one_dim_kernel(const __grid_constant__
                 } else {
                     T slope = O::div(O::sub(y1, y0), O::sub(x1, x0));
                     T dx = O::sub(loc, x0);
-                    v = O::add(y0, O::mul(slope, dx));
+                    v = muladd(slope, dx, y0);  // fused under the fma feature (one_dim/linear.rs:30-35)
                 }
             } break;
             case 2: v = extrap == kOutsideHigh ? y1 : y0; break;  // Left1D

@@ -26,6 +26,9 @@ KINDS_1D = {"linear": 0, "linear_hold_last": 1, "left": 2, "right": 3, "nearest"
 ORDERS = {"reference": 0, "flattened": 1, "recursive": 2}
 
 NO_BAD = np.iinfo(np.uint64).max
+# Arithmetic the checks run in when a test does not say: the flavour of the library under test
+# (interpn_b200/_lib.py reads the same variable), so the whole GPU suite can be re-run against the `fma` build.
+DEFAULT_FMA = os.environ.get("INTERPN_B200_ARITHMETIC", "strict").lower() == "fma"
 
 
 def build(force: bool = False) -> str:
@@ -96,7 +99,7 @@ def interpn_regular(
     out: np.ndarray | None = None,
     *,
     linearize_extrapolation: bool = True,
-    fma: bool = False,
+    fma: bool | None = None,
     order: str = "reference",
     nthreads: int = 1,
     dtype=None,
@@ -129,7 +132,7 @@ def interpn_regular(
         C.c_int(int(linearize_extrapolation)),
         optrs, olens, C.c_size_t(len(obs_a)),
         out.ctypes.data_as(C.POINTER(ct)), C.c_size_t(out.size),
-        C.c_int(int(fma)), C.c_int(ORDERS[order]), C.c_int(nthreads), C.byref(first_bad),
+        C.c_int(int(DEFAULT_FMA if fma is None else fma)), C.c_int(ORDERS[order]), C.c_int(nthreads), C.byref(first_bad),
     )  # fmt: skip
     if st != 0:
         raise OracleError(st, first_bad.value if first_bad.value != NO_BAD else None)
@@ -144,7 +147,7 @@ def interpn_rectilinear(
     out: np.ndarray | None = None,
     *,
     linearize_extrapolation: bool = True,
-    fma: bool = False,
+    fma: bool | None = None,
     order: str = "reference",
     nthreads: int = 1,
     dtype=None,
@@ -170,14 +173,14 @@ def interpn_rectilinear(
         C.c_int(int(linearize_extrapolation)),
         optrs, olens, C.c_size_t(len(obs_a)),
         out.ctypes.data_as(C.POINTER(ct)), C.c_size_t(out.size),
-        C.c_int(int(fma)), C.c_int(ORDERS[order]), C.c_int(nthreads),
+        C.c_int(int(DEFAULT_FMA if fma is None else fma)), C.c_int(ORDERS[order]), C.c_int(nthreads),
     )  # fmt: skip
     if st != 0:
         raise OracleError(st)
     return out
 
 
-def one_dim_regular(kind: str, start, step, vals, locs, out=None, *, fma: bool = False, dtype=None) -> np.ndarray:
+def one_dim_regular(kind: str, start, step, vals, locs, out=None, *, fma: bool | None = None, dtype=None) -> np.ndarray:
     """``Kind1D::new(RegularGrid1D::new(start, step, vals)?).eval(locs, out)`` (one_dim/mod.rs:41-138)."""
     dtype = np.dtype(dtype or np.asarray(vals).dtype)
     sfx, ct = _suffix(dtype)
@@ -192,14 +195,14 @@ def one_dim_regular(kind: str, start, step, vals, locs, out=None, *, fma: bool =
         vals_a.ctypes.data_as(C.POINTER(ct)), C.c_size_t(vals_a.size),
         locs_a.ctypes.data_as(C.POINTER(ct)), C.c_size_t(locs_a.size),
         out.ctypes.data_as(C.POINTER(ct)), C.c_size_t(out.size),
-        C.c_int(int(fma)), C.byref(first_bad),
+        C.c_int(int(DEFAULT_FMA if fma is None else fma)), C.byref(first_bad),
     )  # fmt: skip
     if st != 0:
         raise OracleError(st, first_bad.value if first_bad.value != NO_BAD else None)
     return out
 
 
-def one_dim_rectilinear(kind: str, grid, vals, locs, out=None, *, fma: bool = False, dtype=None) -> np.ndarray:
+def one_dim_rectilinear(kind: str, grid, vals, locs, out=None, *, fma: bool | None = None, dtype=None) -> np.ndarray:
     """``Kind1D::new(RectilinearGrid1D::new(grid, vals)?).eval(locs, out)`` (one_dim/mod.rs:142-187)."""
     dtype = np.dtype(dtype or np.asarray(vals).dtype)
     sfx, ct = _suffix(dtype)
@@ -214,7 +217,7 @@ def one_dim_rectilinear(kind: str, grid, vals, locs, out=None, *, fma: bool = Fa
         vals_a.ctypes.data_as(C.POINTER(ct)), C.c_size_t(vals_a.size),
         locs_a.ctypes.data_as(C.POINTER(ct)), C.c_size_t(locs_a.size),
         out.ctypes.data_as(C.POINTER(ct)), C.c_size_t(out.size),
-        C.c_int(int(fma)),
+        C.c_int(int(DEFAULT_FMA if fma is None else fma)),
     )  # fmt: skip
     if st != 0:
         raise OracleError(st)

@@ -30,10 +30,14 @@ def test_library_exports_every_declared_symbol():
     import interpn_b200._lib as L
 
     names = declared_symbols()
-    assert len(names) == 42, sorted(names)
-    lib = ctypes.CDLL(L.LIB_PATH)
-    missing = [n for n in sorted(names) if not hasattr(lib, n)]
-    assert not missing, missing
+    assert len(names) == 43, sorted(names)
+    # both arithmetic flavours of the library export the same ABI and say which one they are
+    here = os.path.dirname(L.LIB_PATH)
+    for fname, flavour in (("libinterpn_b200.so", 0), ("libinterpn_b200_fma.so", 1)):
+        lib = ctypes.CDLL(os.path.join(here, fname))
+        missing = [n for n in sorted(names) if not hasattr(lib, n)]
+        assert not missing, (fname, missing)
+        assert lib.interpn_b200_arithmetic() == flavour
     for sfx in ("f64", "f32"):
         for m in ("linear", "cubic", "nearest"):
             for g in ("regular", "rectilinear"):

@@ -195,13 +195,18 @@ __global__ void __launch_bounds__(kSweepScatterBlock, 1) sweep_scatter_kernel(co
             sorted[loff[kr >> 16] + (kr & 0xffffu)] = (kr & 0xffff0000u) | li;
         }
         __syncthreads();
-        // sorted[j] -> global position of sorted element j (kept in krank, no longer needed), pos and orig
+        // pos in original order (coalesced): position = global base of the tile's run of the key + rank
+        for (unsigned li = tid; li < nt; li += nthr) {
+            const unsigned kr = krank[li];
+            s.pos[i0 + li] = cnt[kr >> 16] + (kr & 0xffffu);
+        }
+        __syncthreads();
+        // sorted[j] -> global position of sorted element j (kept in krank, no longer needed), and orig
         for (unsigned j = tid; j < nt; j += nthr) {
             const unsigned kl = sorted[j];
             const unsigned key = kl >> 16, li = kl & 0xffffu;
             const unsigned p = cnt[key] + (j - loff[key]);
             krank[j] = p;
-            s.pos[i0 + li] = p;
             s.orig[p] = static_cast<unsigned>(i0 + li);
         }
 #pragma unroll 1
@@ -253,7 +258,10 @@ inline bool plan_sweep(const DeviceGrid& g, size_t n, int fp, int row_bytes_scal
     const size_t min_rows = sweep_env("INTERPN_B200_SWEEP_MIN_ROWS", 16);
     if (N < 2 || gathered <= min_bytes || n < min_points || static_cast<size_t>(rows) < min_rows) return false;
     if (g.nvals >= (size_t(1) << 31) || (g.rect && !axes_in_smem)) return false;
-    const size_t slab_kb = sweep_env("INTERPN_B200_SWEEP_SLAB_KB", 12288);
+    // Slab of the gathered array under one key. Multilinear evaluation is cheap next to the sort, and fewer, larger
+    // slabs mean longer runs per (tile, key) in the scatter: 48 MB measured best on C4 (6.1 -> 7.2 G points/s; 96 MB
+    // falls out of L2). The multicubic kernels dominate their sort and are flat between 6 and 24 MB.
+    const size_t slab_kb = sweep_env("INTERPN_B200_SWEEP_SLAB_KB", fp == 2 ? 49152 : 12288);
     const double target = slab_kb ? static_cast<double>(slab_kb << 10) : 128.0;  // 0: as fine as it gets (tests)
     double slab = static_cast<double>(gathered);
     int bins = 1;

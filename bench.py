@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--arithmetic", default=os.environ.get("INTERPN_B200_ARITHMETIC", "strict"), choices=["strict", "fma"],
                     help="reference build whose arithmetic is reproduced: crate default features (strict, the headline) "
                          "or the crate's `fma` feature = the Python wheel's build (libinterpn_b200_fma.so)")  # fmt: skip
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"], help="element type (the headline metric is f64; C5 names both)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -248,9 +249,9 @@ def run_b200(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    w = W.get(args.workload)
+    w = W.get(args.workload, np.float32 if args.dtype == "f32" else np.float64)
     n = args.points or min(w.n_full, 100_000_000)
-    tdtype = torch.float64
+    tdtype = torch.float32 if args.dtype == "f32" else torch.float64
 
     # ---- grid: built on rank 0, replicated once by an NCCL broadcast straight into each rank's
     # resident storage (the only collective; none on the evaluation path).
@@ -258,7 +259,7 @@ def run_b200(args):
     from interpn_b200 import sharding
 
     spec = sharding.GridSpec(
-        w.method, w.rect, "float64", bool(w.linearize), dims=list(w.dims),
+        w.method, w.rect, "float32" if args.dtype == "f32" else "float64", bool(w.linearize), dims=list(w.dims),
         starts=None if w.rect else [float(v) for v in w.starts], steps=None if w.rect else [float(v) for v in w.steps],
         grids=[[float(v) for v in g] for g in w.grids] if w.rect else None,
     )  # fmt: skip
@@ -342,7 +343,7 @@ def run_b200(args):
             vals_h = interp.vals_tensor().cpu().numpy()
             want = cpu_eval(oracle, w, vals_h, o, max(1, oracle.max_threads()))
             got = out[sl].contiguous().cpu().numpy()
-            parity = {"sample_points": int(got.size), "bit_identical": bool(np.array_equal(got.view(np.uint64), want.view(np.uint64))),
+            parity = {"sample_points": int(got.size), "bit_identical": bool(np.array_equal(got.view(np.uint32 if got.dtype == np.float32 else np.uint64), want.view(np.uint32 if want.dtype == np.float32 else np.uint64))),
                       "max_abs_diff": float(np.max(np.abs(got - want)))}
         except Exception as e:  # the oracle is a checker, never a dependency of the measured path
             parity = {"error": repr(e)}
@@ -413,7 +414,7 @@ def run_b200(args):
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
-        "dtype": "f64",
+        "dtype": args.dtype,
         "data": "synthetic",
         "config": {
             "workload": w.name,
@@ -424,7 +425,7 @@ def run_b200(args):
             "out_of_bounds_fraction": w.oob_fraction,
             "linearize_extrapolation": bool(w.linearize),
             "arithmetic": args.arithmetic,
-            "l2": f"query arrays ({n * (w.ndims + 1) * 8 / 1e9:.2f} GB per step) exceed L2; the {w.nvals * 8 / 1e6:.0f} MB grid is reused across steps by design",
+            "l2": f"query arrays ({n * (w.ndims + 1) * w.dtype.itemsize / 1e9:.2f} GB per step) exceed L2; the {w.nvals * w.dtype.itemsize / 1e6:.0f} MB grid is reused across steps by design",
             "parallelism": f"query batch sharded over {world} GPU(s), grid replicated by one NCCL broadcast" if distributed else "single GPU",
         },
         "roofline": roofline,

@@ -219,6 +219,38 @@ __device__ __forceinline__ T cdn_sum(T a, T b, T c, T d) {
     return muladd(a, b, Ops<T>::mul(c, d));
 }
 
+// ---- f32 twins of the three division-free pieces -------------------------------------------------------------
+// Same arguments with the f32 constants: the approximate quotient is within 2^-23 |Q| of Q = d/step, so an unclamped
+// f~ is proven by 0 <= fmaf(-f~, step, d) <= step*(1 - 2^-11) when |f~| < 2^12 (|RN(Q) - Q| <= 2^-24 * 2^12), a clamped
+// one needs |f~| <= 2^22; 0.5f has an even significand and ulp 2^-24 above it, so RN(y) <= 0.5 <=> y <= 0.5 + 2^-25;
+// Markstein's theorem is precision-independent (guard: operands within [2^-60, 2^60), or a zero numerator).
+// Host preconditions (launch_common.cuh make_args -> fast_div): 2^-60 <= step < 2^60 and every dim <= 4096.
+__device__ __forceinline__ bool fast_cell(float x, float start, float step, float rstep, float lim, int dim, int& origin,
+                                          float& od, float& d) {
+    d = __fsub_rn(x, start);
+    const float q = __fmul_rn(d, rstep);
+    const int f = __float2int_rd(q);
+    origin = min(max(f, 0), dim - 2);
+    od = __int2float_rn(origin);
+    const float r = __fmaf_rn(-od, step, d);
+    const bool proven = r >= 0.0f && r <= lim;
+    const bool sane = static_cast<unsigned>(f) + (1u << 22) <= (1u << 23);
+    return origin == f ? proven : sane;
+}
+__device__ __forceinline__ bool nearest_upper(float e, float hstep, float tau) { return !(__fsub_rn(e, hstep) <= tau); }
+__device__ __forceinline__ bool markstein_operand_ok(float a) {
+    const unsigned bits = static_cast<unsigned>(__float_as_int(a));
+    const unsigned e = (bits >> 23) & 0xffu;
+    return (e - 67u <= 119u) || ((bits << 1) == 0u);  // 2^-60 <= |a| < 2^60, or +-0
+}
+__device__ __forceinline__ float markstein_div(float a, float b, float rb) {
+    const float q0 = __fmul_rn(a, rb);
+    const float e0 = __fmaf_rn(-q0, b, a);
+    const float q1 = __fmaf_rn(e0, rb, q0);
+    const float e1 = __fmaf_rn(-q1, b, a);
+    return copysignf(__fmaf_rn(e1, rb, q1), a);
+}
+
 // ref: multicubic/mod.rs:72-91. c2 = b - (a+a) is issued as fma(-2, a, b): a+a is exact, so the bits are the same
 // in both flavours. The polynomial is y0 + t*(c1 + t*(c2 + t*c3)), three chained mul_add under the fma feature.
 template <class T>

@@ -327,22 +327,21 @@ __device__ __forceinline__ bool nearest_locate(const EvalArgs<T, N>& a, const T*
     return ok;
 }
 
-// Division-free twins of linear_locate / nearest_locate for regular f64 grids (device_math.cuh
-// fast_cell & co.). They return false when a point needs the exact path; `base` / `idx` stay in range
-// either way.
-template <int N, class I>
-__device__ __forceinline__ bool linear_locate_fast(const EvalArgs<double, N>& a, const double (&xs)[N], double (&t)[N],
-                                                   I& base) {
+// Division-free twins of linear_locate / nearest_locate for regular grids (device_math.cuh fast_cell & co., f64 and
+// f32). They return false when a point needs the exact path; `base` / `idx` stay in range either way.
+template <class T, int N, class I>
+__device__ __forceinline__ bool linear_locate_fast(const EvalArgs<T, N>& a, const T (&xs)[N], T (&t)[N], I& base) {
+    using O = Ops<T>;
     const I(&stride)[N] = strides_of<I>(a);
     bool sure = a.fast_div != 0;
     base = 0;
 #pragma unroll
     for (int d = 0; d < N; ++d) {
         int origin;
-        double od, dd;
-        sure = fast_cell(xs[d], a.start[d], a.step[d], a.rstep[d], a.lim[d], a.dim[d], origin, od, dd) && sure;
-        const double x0 = muladd<(N <= 6)>(a.step[d], od, a.start[d]);
-        const double e = __dsub_rn(xs[d], x0);
+        T od, dd;
+        sure = fast_cell(xs[d], a.start[d], a.step[d], a.rstep[d], static_cast<T>(a.lim[d]), a.dim[d], origin, od, dd) && sure;
+        const T x0 = muladd<(N <= 6)>(a.step[d], od, a.start[d]);
+        const T e = O::sub(xs[d], x0);
         sure = markstein_operand_ok(e) && sure;
         t[d] = markstein_div(e, a.step[d], a.rstep[d]);
         base += static_cast<I>(origin) * stride[d];
@@ -350,19 +349,20 @@ __device__ __forceinline__ bool linear_locate_fast(const EvalArgs<double, N>& a,
     return sure;
 }
 
-template <int N, class I>
-__device__ __forceinline__ bool nearest_locate_fast(const EvalArgs<double, N>& a, const double (&xs)[N], I& idx) {
+template <class T, int N, class I>
+__device__ __forceinline__ bool nearest_locate_fast(const EvalArgs<T, N>& a, const T (&xs)[N], I& idx) {
+    using O = Ops<T>;
     const I(&stride)[N] = strides_of<I>(a);
     bool sure = a.fast_div != 0;
     idx = 0;
 #pragma unroll
     for (int d = 0; d < N; ++d) {
         int origin;
-        double od, dd;
-        sure = fast_cell(xs[d], a.start[d], a.step[d], a.rstep[d], a.lim[d], a.dim[d], origin, od, dd) && sure;
-        const double x0 = muladd(a.step[d], od, a.start[d]);
-        const double e = __dsub_rn(xs[d], x0);
-        const int off = nearest_upper(e, a.hstep[d], a.tau[d]) ? 1 : 0;
+        T od, dd;
+        sure = fast_cell(xs[d], a.start[d], a.step[d], a.rstep[d], static_cast<T>(a.lim[d]), a.dim[d], origin, od, dd) && sure;
+        const T x0 = muladd(a.step[d], od, a.start[d]);
+        const T e = O::sub(xs[d], x0);
+        const int off = nearest_upper(e, static_cast<T>(a.hstep[d]), static_cast<T>(a.tau[d])) ? 1 : 0;
         idx += static_cast<I>(origin + off) * stride[d];
     }
     return sure;
@@ -372,16 +372,16 @@ __device__ __forceinline__ bool nearest_locate_fast(const EvalArgs<double, N>& a
 template <class T, int N, bool RECT, class I>
 __device__ __forceinline__ bool linear_locate_any(const EvalArgs<T, N>& a, const T* __restrict__ axes, const T (&xs)[N],
                                                   T (&t)[N], I& base) {
-    if constexpr (!RECT && sizeof(T) == 8) {
-        if (linear_locate_fast<N, I>(a, xs, t, base)) return true;
+    if constexpr (!RECT) {
+        if (linear_locate_fast<T, N, I>(a, xs, t, base)) return true;
     }
     return linear_locate<T, N, RECT, I>(a, axes, xs, t, base);
 }
 template <class T, int N, bool RECT, class I>
 __device__ __forceinline__ bool nearest_locate_any(const EvalArgs<T, N>& a, const T* __restrict__ axes, const T (&xs)[N],
                                                    I& idx) {
-    if constexpr (!RECT && sizeof(T) == 8) {
-        if (nearest_locate_fast<N, I>(a, xs, idx)) return true;
+    if constexpr (!RECT) {
+        if (nearest_locate_fast<T, N, I>(a, xs, idx)) return true;
     }
     return nearest_locate<T, N, RECT, I>(a, axes, xs, idx);
 }

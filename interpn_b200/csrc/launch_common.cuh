@@ -36,16 +36,19 @@ inline EvalArgs<T, N> make_args(const DeviceGrid& g, const T* const* obs, size_t
     a.vals = static_cast<const T*>(g.vals);
     a.win = static_cast<const T*>(g.win);
     a.fast_div = 0;
-    if (!g.rect && sizeof(T) == 8) {
-        // exact_div's divisor guard (device_math.cuh): 2^-300 <= step < 2^301 on every dimension
+    if (!g.rect) {
+        // guards of the division-free sequences (device_math.cuh): f64 2^-300 <= step < 2^301 and dim < 2^30;
+        // f32 2^-60 <= step < 2^60 and dim <= 4096 (the remainder proof needs |cell| * 2^-24 < 2^-12)
         a.fast_div = 1;
+        const double lo = sizeof(T) == 8 ? 0x1p-300 : 0x1p-60, hi = sizeof(T) == 8 ? 0x1p301 : 0x1p60;
+        const int max_dim = sizeof(T) == 8 ? (1 << 30) - 1 : 4096;
         for (int d = 0; d < N; ++d)
-            if (!(g.step[d] >= 0x1p-300 && g.step[d] < 0x1p301) || g.dim[d] >= (1 << 30)) a.fast_div = 0;
+            if (!(g.step[d] >= lo && g.step[d] < hi) || g.dim[d] > max_dim) a.fast_div = 0;
     }
-    for (int d = 0; d < N; ++d) {  // exact: power-of-two scalings of a step in the guarded range
+    for (int d = 0; d < N; ++d) {  // exact: power-of-two scalings of a step in the guarded range (lim: rounded, with slack)
         a.hstep[d] = g.step[d] * 0.5;
-        a.tau[d] = g.step[d] * 0x1p-54;
-        a.lim[d] = g.step[d] * (1.0 - 0x1p-20);
+        a.tau[d] = g.step[d] * (sizeof(T) == 8 ? 0x1p-54 : 0x1p-25);
+        a.lim[d] = g.step[d] * (sizeof(T) == 8 ? 1.0 - 0x1p-20 : 1.0 - 0x1p-11);
     }
     a.axes = static_cast<const T*>(g.axes);
     a.axes_total = g.axes_total;

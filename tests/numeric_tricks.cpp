@@ -172,6 +172,63 @@ int main(int argc, char** argv) {
             if (bits(std::fma(e1, rq, q1)) != bits(num / qq)) FAIL("bare sequence: a=%a b=%a", num, qq);
         }
     }
+    // ---- f32 twins (device_math.cuh): fast_cell / nearest_upper / markstein_div in float against float IEEE ops ----
+    {
+        auto fbits = [](float x) { uint32_t b; memcpy(&b, &x, 4); return b; };
+        auto ffrom = [](uint32_t b) { float x; memcpy(&x, &b, 4); return x; };
+        auto fnudge = [&](float x, int k) { return ffrom(fbits(x) + (int32_t)k); };
+        long checked32 = 0;
+        for (long it = 0; it < trials / 3; ++it) {
+            const float step = (float)std::ldexp(0.5 + u01(), (int)(rnd() % 41) - 20);
+            const float rstep = 1.0f / step;
+            const float start = (float)((u01() - 0.5) * std::ldexp(1.0, (int)(rnd() % 24) - 8));
+            const int dim = 2 + (int)(rnd() % 4095);  // <= 4096: the host's precondition
+            const float hstep = step * 0.5f, tau = (float)((double)step * 0x1p-25), lim = (float)((double)step * (1.0 - 0x1p-11));
+            const int k = (int)(rnd() % (unsigned)dim);
+            float x;
+            switch (rnd() % 6) {
+                case 0: x = start + step * (float)k; break;
+                case 1: x = fnudge(start + step * (float)k, (int)(rnd() % 9) - 4); break;
+                case 2: x = fnudge(start + step * (float)k + hstep, (int)(rnd() % 9) - 4); break;
+                case 3: x = fnudge((start + step * (float)k) + hstep, (int)(rnd() % 5) - 2); break;
+                default: x = start + step * (float)(dim - 1) * (float)(1.6 * u01() - 0.3); break;
+            }
+            // reference (multilinear/regular.rs:414-425 in f32)
+            const float qref = std::floor((x - start) / step);
+            long long iref = (long long)qref;
+            int o_ref = (int)(iref < 0 ? 0 : (iref > dim - 2 ? dim - 2 : iref));
+            // fast_cell (float)
+            const float d = x - start;
+            const float q = d * rstep;
+            int f = (q != q) ? 0 : (int)std::floor(q);
+            int origin = f < 0 ? 0 : (f > dim - 2 ? dim - 2 : f);
+            const float od = (float)origin;
+            const float r = std::fmaf(-od, step, d);
+            const bool proven = r >= 0.0f && r <= lim;
+            const bool sane = (unsigned)f + (1u << 22) <= (1u << 23);
+            if (origin == f ? proven : sane) {
+                if (o_ref != origin) FAIL("fast_cell f32: x=%a start=%a step=%a dim=%d ref=%d fast=%d", x, start, step, dim, o_ref, origin);
+                const float x0 = start + step * od;
+                const float e = x - x0;
+                const bool up_ref = !((e / step) <= 0.5f);
+                if ((!((e - hstep) <= tau)) != up_ref) FAIL("nearest_upper f32: e=%a step=%a", e, step);
+                const uint32_t eb = fbits(e);
+                if ((((eb >> 23) & 0xffu) - 67u <= 119u) || ((eb << 1) == 0u)) {
+                    const float q0 = e * rstep, e0 = std::fmaf(-q0, step, e), q1 = std::fmaf(e0, rstep, q0), e1 = std::fmaf(-q1, step, e);
+                    const float t = std::copysign(std::fmaf(e1, rstep, q1), e), t_ref = e / step;
+                    if (fbits(t) != fbits(t_ref)) FAIL("markstein f32: e=%a step=%a got=%a want=%a", e, step, t, t_ref);
+                }
+                ++checked32;
+            }
+        }
+        if (checked32 < trials / 4) FAIL("f32 fast path proved only %ld of %ld", checked32, trials / 3);
+        const float fsteps[] = {1.0f, 0.1f, 100.0f / 99.0f, 0.125f, 3.0f, 1e-3f, 12345.678f};
+        for (float step : fsteps)
+            for (int k = -64; k <= 64; ++k) {
+                const float e = fnudge(step * 0.5f, k);
+                if ((!((e - step * 0.5f) <= (float)((double)step * 0x1p-25))) != !((e / step) <= 0.5f)) FAIL("f32 tie sweep: e=%a step=%a", e, step);
+            }
+    }
     // exhaustive neighbourhood of the tie for a few steps: e = step/2 + k ulps, k = -64..64
     const double steps[] = {1.0, 0.1, 100.0 / 99.0, 0.125, 3.0, 1e-7, 12345.678, 0x1.fffffffffffffp+3, 0x1.0000000000001p-5};
     for (double step : steps)

@@ -400,7 +400,10 @@ __global__ void __launch_bounds__(kBlock, MINB) cubic_quad4_kernel(const __grid_
     static_assert(N >= 2 && N <= 4, "quad-cooperative cubic covers N = 2..4");
     using Slot = QuadSlot<T, N, RECT>;
     constexpr int kWarps = kBlock / 32;
-    constexpr int kUnrollP = (!RECT && N <= 3) ? 4 : 1;
+#ifndef IB200_QUAD4_UNROLL3
+#define IB200_QUAD4_UNROLL3 4
+#endif
+    constexpr int kUnrollP = (!RECT && N <= 3) ? IB200_QUAD4_UNROLL3 : 1;
     constexpr int kSlotWarpBytes = quad4_slot_warp_bytes<T, N, RECT>();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const T* axes = nullptr;

@@ -130,7 +130,11 @@ __device__ __forceinline__ void load_row(const T* __restrict__ vals, const T* __
 #pragma unroll
         for (int j = 0; j < W; ++j) r[j] = __ldg(vals + idx + j);
     } else if constexpr (sizeof(T) == 8 && W == 4) {
+#ifdef IB200_LDG_NOALLOC
+        asm("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+#else
         asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+#endif
             : "=d"(r[0]), "=d"(r[1]), "=d"(r[2]), "=d"(r[3])
             : "l"(win + static_cast<long long>(idx) * 4));
     } else if constexpr (sizeof(T) == 8 && W == 2) {

@@ -481,35 +481,78 @@ int rect_new(int method, const T* const* grids, const size_t* grid_lens, size_t 
     if (sorted) {
         for (size_t d = 0; d < ngrids; ++d) {
             const size_t n = grid_lens[d];
-            g.rc_off[d] = static_cast<int>(packed.size());
-            for (size_t i = 0; i + 1 < n; ++i) {
-                volatile T w = grids[d][i + 1] - grids[d][i];  // the kernels' divisor, rounded in T
-                packed.push_back(static_cast<T>(T(1) / w));
-            }
-            size_t nb = 2 * n;
-            if (nb > 65536) nb = 65536;
-            std::vector<int> lut(nb + 1);
             const double g0 = static_cast<double>(grids[d][0]), span = static_cast<double>(grids[d][n - 1]) - g0;
-            lut[0] = 0;
-            lut[nb] = static_cast<int>(n);
-            for (size_t k = 1; k < nb; ++k) {
-                const double edge = g0 + span * (static_cast<double>(k) / static_cast<double>(nb));
-                size_t lo = 0, hi = n;
-                while (lo < hi) {
-                    const size_t mid = (lo + hi) / 2;
-                    if (static_cast<double>(grids[d][mid]) < edge) lo = mid + 1;
-                    else hi = mid;
+            auto append_ints = [&](const std::vector<int>& v) {
+                const size_t slots = (v.size() * sizeof(int) + sizeof(T) - 1) / sizeof(T);
+                const size_t at = packed.size();
+                packed.resize(at + slots, T(0));
+                memcpy(packed.data() + at, v.data(), v.size() * sizeof(int));
+            };
+            if (method == INTERPN_B200_LINEAR) {  // reciprocal cell widths: the divisor table of t = (x - g0)/(g1 - g0)
+                g.rc_off[d] = static_cast<int>(packed.size());
+                for (size_t i = 0; i + 1 < n; ++i) {
+                    volatile T w = grids[d][i + 1] - grids[d][i];  // the kernels' divisor, rounded in T
+                    packed.push_back(static_cast<T>(T(1) / w));
                 }
-                lut[k] = static_cast<int>(lo);
             }
-            g.lut_off[d] = static_cast<int>(packed.size());
-            g.lut_nb[d] = static_cast<int>(nb);
-            g.lut_scale[d] = static_cast<double>(nb) / span;
-            const size_t slots = ((nb + 1) * sizeof(int) + sizeof(T) - 1) / sizeof(T);
-            const size_t at = packed.size();
-            packed.resize(at + slots, T(0));
-            memcpy(packed.data() + at, lut.data(), (nb + 1) * sizeof(int));
+            if (method != INTERPN_B200_NEAREST) {
+                // bucket table of the search (kernels.cuh rect_lower_bound): lut[k] = partition_point(g < edge_k)
+                size_t nb = 2 * n;
+                if (nb > 65536) nb = 65536;
+                std::vector<int> lut(nb + 1);
+                lut[0] = 0;
+                lut[nb] = static_cast<int>(n);
+                for (size_t k = 1; k < nb; ++k) {
+                    const double edge = g0 + span * (static_cast<double>(k) / static_cast<double>(nb));
+                    size_t lo = 0, hi = n;
+                    while (lo < hi) {
+                        const size_t mid = (lo + hi) / 2;
+                        if (static_cast<double>(grids[d][mid]) < edge) lo = mid + 1;
+                        else hi = mid;
+                    }
+                    lut[k] = static_cast<int>(lo);
+                }
+                g.lut_off[d] = static_cast<int>(packed.size());
+                g.lut_nb[d] = static_cast<int>(nb);
+                g.lut_scale[d] = static_cast<double>(nb) / span;
+                append_ints(lut);
+            }
         }
+        g.axes_core = static_cast<int>(packed.size());  // what a kernel that does not use the cell tables stages
+        for (size_t d = 0; d < ngrids; ++d) {
+            const size_t n = grid_lens[d];
+            const double g0 = static_cast<double>(grids[d][0]), span = static_cast<double>(grids[d][n - 1]) - g0;
+            auto append_ints = [&](const std::vector<int>& v) {
+                const size_t slots = (v.size() * sizeof(int) + sizeof(T) - 1) / sizeof(T);
+                const size_t at = packed.size();
+                packed.resize(at + slots, T(0));
+                memcpy(packed.data() + at, v.data(), v.size() * sizeof(int));
+            };
+            if (method != INTERPN_B200_CUBIC) {
+                // cell table of the multilinear / nearest kernels (kernels.cuh rect_cell_locate): four buckets per node,
+                // clut[b] = the cell that contains the left edge of bucket b
+                size_t nb = 4 * n;
+                if (nb > 65536) nb = 65536;
+                std::vector<int> clut(nb);
+                for (size_t k = 0; k < nb; ++k) {
+                    const double edge = g0 + span * (static_cast<double>(k) / static_cast<double>(nb));
+                    size_t lo = 0, hi = n;  // number of nodes <= edge
+                    while (lo < hi) {
+                        const size_t mid = (lo + hi) / 2;
+                        if (static_cast<double>(grids[d][mid]) <= edge) lo = mid + 1;
+                        else hi = mid;
+                    }
+                    const long c = static_cast<long>(lo) - 1;
+                    clut[k] = static_cast<int>(c < 0 ? 0 : (c > static_cast<long>(n) - 2 ? static_cast<long>(n) - 2 : c));
+                }
+                g.clut_off[d] = static_cast<int>(packed.size());
+                g.clut_nb[d] = static_cast<int>(nb);
+                g.clut_scale[d] = static_cast<double>(nb) / span;
+                append_ints(clut);
+            }
+        }
+        if (method != INTERPN_B200_CUBIC) g.rect_cell = 1;
+        if (method == INTERPN_B200_NEAREST) g.rect_fast = 0;  // no bucket table is built for nearest
     }
     if (sorted && method == INTERPN_B200_CUBIC) {
         for (size_t d = 0; d < ngrids; ++d) {

@@ -34,6 +34,7 @@ struct DeviceGrid {
     int win_cross = 0;         // cubic, N = 2..4: the cross-window layout of kernels.cuh cubic_quad_point
     void* axes = nullptr;           // device, all rectilinear axes packed back to back
     int axis_off[kMaxNd] = {};      // element offset of axis d inside `axes`
+    int axes_core = 0;              // elements of the blob before the cell tables (kernels that do not read them stage only this)
     int axes_total = 0;             // elements of the whole blob: axes, then reciprocal cell widths, then bucket tables
     int rect_fast = 0;              // axes strictly increasing and finite: bucket-table search is valid
     int rect_fast_div = 0;          // ... and (f64) every cell width within exact_div's range
@@ -41,6 +42,10 @@ struct DeviceGrid {
     int lut_off[kMaxNd] = {};       // element offset of axis d's bucket table (lut_nb+1 ints)
     int lut_nb[kMaxNd] = {};
     double lut_scale[kMaxNd] = {};  // buckets per unit length
+    int rect_cell = 0;              // linear / nearest, strictly increasing finite axes: cell tables present (search replaced)
+    int clut_off[kMaxNd] = {};      // element offset of axis d's cell table (clut_nb ints)
+    int clut_nb[kMaxNd] = {};
+    double clut_scale[kMaxNd] = {}; // buckets per unit length
     int rect_cubic_table = 0;       // cubic, strictly increasing finite axes: per-cell constant table present
     int ct_off[kMaxNd] = {};        // element offset of axis d's cubic cell table (dim+1 rows of 12 elements, 16-byte aligned)
     int sm_count = 148;

@@ -32,6 +32,8 @@ struct EvalArgs {
     int axes_total;   // rectilinear: elements of the blob (axes, reciprocal cell widths, bucket tables)
     int rect_fast, rect_fast_div;  // rectilinear: search / division accelerators are valid (capi.cu rect_new)
     int rc_off[N], lut_off[N], lut_nb[N];
+    int rect_cell, clut_off[N], clut_nb[N];  // rectilinear linear / nearest: cell tables (rect_cell_locate)
+    T clut_scale[N];
     int ct_off[N];  // rectilinear cubic: per-cell constant tables (capi.cu cubic_cell_table), valid when rect_cubic_table
     int rect_cubic_table;
     T lut_scale[N];
@@ -85,6 +87,44 @@ __device__ __forceinline__ int rect_lower_bound(const EvalArgs<T, N>& a, const T
         len = below ? len - half - 1 : half;
     }
     return lo;
+}
+
+// Cell of x on a strictly increasing axis, for the multilinear / nearest kernels: origin = clamp(partition_point(g < x)
+// - 1, 0, n-2) and its two nodes, from THREE shared-memory loads (the bucket search above costs 5-6, and these kernels
+// sit on the shared-memory wavefront rate: ncu l1tex 93 %, profiles/r1_p5_c5n3_rect_ncu.json). A table with four
+// buckets per node gives the cell c0 that contains the bucket's left edge; with at most one node inside a bucket the
+// answer is c0 or c0+1, decided by g[c0+1] < x, and the third load (g[c0] or g[c0+2]) both completes the cell and
+// PROVES it: the chosen cell must satisfy g[c] < x <= g[c+1] (or be the clamped end cell). Anything else — a bucket
+// index off by one at a bucket edge, two nodes in one bucket — fails the proof and takes the plain bisection.
+// NaN lands in cell 0 like slice::partition_point (every compare false).
+// The rare unproven point: plain bisection of the whole axis (inline: an out-of-line call cost the callers a stack frame).
+template <class T>
+static __device__ __forceinline__ int rect_cell_bisect(const T* __restrict__ g, int n, T x) {
+    return clamp_cell(lower_bound(g, n, x) - 1, n - 2);
+}
+
+template <class T, int N>
+__device__ __forceinline__ int rect_cell_locate(const EvalArgs<T, N>& a, const T* __restrict__ axes, int d, T x, T& g0, T& g1) {
+    const T* g = axes + a.axis_off[d];
+    const int n = a.dim[d];
+    if (a.rect_cell) {
+        const int* lut = reinterpret_cast<const int*>(axes + a.clut_off[d]);
+        const int b = min(max(Ops<T>::floor_sat((x - g[0]) * a.clut_scale[d]), 0), a.clut_nb[d] - 1);
+        const int c0 = lut[b];
+        const T gb = g[c0 + 1];
+        const bool up = gb < x && c0 < n - 2;
+        const T other = g[up ? c0 + 2 : c0];
+        const bool proven = up ? (!(other < x) || c0 + 1 == n - 2) : (other < x || c0 == 0);
+        if (proven) {
+            g0 = up ? gb : other;
+            g1 = up ? other : gb;
+            return c0 + (up ? 1 : 0);
+        }
+    }
+    const int origin = a.rect_cell ? rect_cell_bisect<T>(g, n, x) : clamp_cell(rect_lower_bound<T, N>(a, axes, d, x) - 1, n - 2);
+    g0 = g[origin];
+    g1 = g[origin + 1];
+    return origin;
 }
 
 // Records an unrepresentable query point: the smallest failing index of the caller's batch wins.
@@ -255,7 +295,10 @@ __device__ __forceinline__ T linear_tree(const T* __restrict__ vals, const T* __
 
 // Locate one query point: per-dimension cell origin -> flat index of the footprint's first corner,
 // and the normalized coordinates t. Returns false for an unrepresentable coordinate (regular grids).
-template <class T, int N, bool RECT, class I>
+// CELL: rectilinear axes are located through the cell table (rect_cell_locate) — used by the kernels that gather from
+// an L2-resident window copy; the kernels for grids beyond L2 are DRAM-bound, gain nothing from a cheaper search and
+// lost 5 % to its extra live registers (C3-linear), so they keep the bucket search.
+template <class T, int N, bool RECT, class I, bool CELL = false>
 __device__ __forceinline__ bool linear_locate(const EvalArgs<T, N>& a, const T* __restrict__ axes, const T (&xs)[N],
                                               T (&t)[N], I& base) {
     const I(&stride)[N] = strides_of<I>(a);
@@ -267,10 +310,15 @@ __device__ __forceinline__ bool linear_locate(const EvalArgs<T, N>& a, const T* 
         const T x = xs[d];
         int origin;
         if constexpr (RECT) {
-            const T* g = axes + a.axis_off[d];
-            origin = clamp_cell(rect_lower_bound<T, N>(a, axes, d, x) - 1, a.dim[d] - 2);
-            const T x0 = g[origin];
-            const T x1 = g[origin + 1];
+            T x0, x1;
+            if constexpr (CELL) {
+                origin = rect_cell_locate<T, N>(a, axes, d, x, x0, x1);
+            } else {
+                const T* g = axes + a.axis_off[d];
+                origin = clamp_cell(rect_lower_bound<T, N>(a, axes, d, x) - 1, a.dim[d] - 2);
+                x0 = g[origin];
+                x1 = g[origin + 1];
+            }
             const T e = O::sub(x, x0), h = O::sub(x1, x0);
             if constexpr (sizeof(T) == 8) {
                 // the cell's reciprocal width is tabulated: exact_div instead of the IEEE division
@@ -306,10 +354,8 @@ __device__ __forceinline__ bool nearest_locate(const EvalArgs<T, N>& a, const T*
         int origin;
         T dt;
         if constexpr (RECT) {
-            const T* g = axes + a.axis_off[d];
-            origin = clamp_cell(rect_lower_bound<T, N>(a, axes, d, x) - 1, a.dim[d] - 2);
-            const T x0 = g[origin];
-            const T x1 = g[origin + 1];
+            T x0, x1;
+            origin = rect_cell_locate<T, N>(a, axes, d, x, x0, x1);
             const T e = O::sub(x, x0), h = O::sub(x1, x0);
             if constexpr (sizeof(T) == 8) {
                 if (a.rect_fast_div) {  // division-free and exact: device_math.cuh nearest_upper
@@ -317,7 +363,8 @@ __device__ __forceinline__ bool nearest_locate(const EvalArgs<T, N>& a, const T*
                     continue;
                 }
             }
-            dt = O::div(e, h);
+            if constexpr (sizeof(T) == 8) dt = exact_div_slow(e, h);  // axes outside the guarded range only: out of line
+            else dt = O::div(e, h);
         } else {
             int iloc = 0;
             ok = floor_cell(x, a.start[d], a.step[d], a.rstep[d], a.fast_div != 0, iloc) && ok;
@@ -373,13 +420,13 @@ __device__ __forceinline__ bool nearest_locate_fast(const EvalArgs<T, N>& a, con
 }
 
 // One point of the streaming kernels: fast path where it exists, exact path otherwise.
-template <class T, int N, bool RECT, class I>
+template <class T, int N, bool RECT, class I, bool CELL = false>
 __device__ __forceinline__ bool linear_locate_any(const EvalArgs<T, N>& a, const T* __restrict__ axes, const T (&xs)[N],
                                                   T (&t)[N], I& base) {
     if constexpr (!RECT) {
         if (linear_locate_fast<T, N, I>(a, xs, t, base)) return true;
     }
-    return linear_locate<T, N, RECT, I>(a, axes, xs, t, base);
+    return linear_locate<T, N, RECT, I, CELL>(a, axes, xs, t, base);
 }
 template <class T, int N, bool RECT, class I>
 __device__ __forceinline__ bool nearest_locate_any(const EvalArgs<T, N>& a, const T* __restrict__ axes, const T (&xs)[N],
@@ -424,7 +471,7 @@ __global__ void __launch_bounds__(kBlock) linear_kernel(const __grid_constant__ 
         for (int p = 0; p < P; ++p) {
             T t[N];
             I base;
-            ok[p] = linear_locate_any<T, N, RECT, I>(a, axes, xs[p], t, base);
+            ok[p] = linear_locate_any<T, N, RECT, I, (WL != 0)>(a, axes, xs[p], t, base);
             all_ok = all_ok && ok[p];
             if (!ok[p]) base = 0;  // keep the gather in range; the value is discarded
             res[p] = linear_tree<T, N, WL, I>(a.vals, a.win, base, stride, t);
@@ -447,7 +494,7 @@ __global__ void __launch_bounds__(kBlock) linear_kernel(const __grid_constant__ 
             for (int d = 0; d < N; ++d) xs[d] = load_query(a.obs[d] + i);
             T t[N];
             I base;
-            if (linear_locate_any<T, N, RECT, I>(a, axes, xs, t, base)) {
+            if (linear_locate_any<T, N, RECT, I, (WL != 0)>(a, axes, xs, t, base)) {
                 store_result(a.out + i, linear_tree<T, N, WL, I>(a.vals, a.win, base, stride, t));
             } else {
                 report_bad(a, i);

@@ -262,7 +262,25 @@ __global__ void __launch_bounds__(kBlock) sweep_unsort_kernel(const __grid_const
                                                               const unsigned* __restrict__ pos, bool regular) {
     const bool any_bad = regular && *reinterpret_cast<volatile unsigned long long*>(a.first_bad) != kNoBad;
     const unsigned long long gstride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
-    for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n; i += gstride) {
+    const unsigned long long gtid = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (!any_bad) {
+        // common case: four dependent (pos -> res) gathers in flight per thread
+        constexpr int U = 4;
+        unsigned long long i = gtid;
+        for (; i + (U - 1) * gstride < a.n; i += U * gstride) {
+            unsigned p[U];
+            T v[U];
+#pragma unroll
+            for (int k = 0; k < U; ++k) p[k] = __ldg(pos + i + k * gstride);
+#pragma unroll
+            for (int k = 0; k < U; ++k) v[k] = __ldcg(res + p[k]);
+#pragma unroll
+            for (int k = 0; k < U; ++k) store_result(a.out + i + k * gstride, v[k]);
+        }
+        for (; i < a.n; i += gstride) store_result(a.out + i, __ldcg(res + __ldg(pos + i)));
+        return;
+    }
+    for (unsigned long long i = gtid; i < a.n; i += gstride) {
         if (any_bad) {
             bool ok = true;
 #pragma unroll

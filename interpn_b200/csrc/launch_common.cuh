@@ -9,6 +9,8 @@ namespace ib200 {
 // resident); larger axes are searched in global memory through L1/L2.
 constexpr int kAxesSmemBudget = 96 * 1024;
 
+size_t sweep_env_common(const char* name, size_t fallback);
+
 template <class T, int N>
 inline EvalArgs<T, N> make_args(const DeviceGrid& g, const T* const* obs, size_t n, T* out,
                                 unsigned long long* first_bad, unsigned long long index_base,
@@ -59,7 +61,8 @@ inline EvalArgs<T, N> make_args(const DeviceGrid& g, const T* const* obs, size_t
     a.rect_fast_div = g.rect_fast_div;
     a.rect_cubic_table = g.rect_cubic_table;
     a.rect_cell = g.rect_cell;
-    a.axes_in_smem = g.rect && static_cast<size_t>(g.axes_total) * sizeof(T) <= kAxesSmemBudget;
+    static const size_t axes_budget = sweep_env_common("INTERPN_B200_AXES_SMEM_KB", kAxesSmemBudget >> 10) << 10;
+    a.axes_in_smem = g.rect && static_cast<size_t>(g.axes_total) * sizeof(T) <= axes_budget;
     a.linearize = g.linearize;
     a.first_bad = first_bad;
     a.index_base = index_base;

@@ -10,6 +10,8 @@ size_t sweep_env(const char* name, size_t fallback) {
     return e && *e ? static_cast<size_t>(strtoull(e, nullptr, 10)) : fallback;
 }
 
+size_t sweep_env_common(const char* name, size_t fallback) { return sweep_env(name, fallback); }
+
 // ---------------------------------------------------------------------------------------------
 // Window layout builder: win[f*W + j] = vals[min(f + j, nvals - 1)]  (kernels.cuh load_row)
 // ---------------------------------------------------------------------------------------------

@@ -464,7 +464,7 @@ int rect_new(int method, const T* const* grids, const size_t* grid_lens, size_t 
     // reference itself checks just the first two nodes (multilinear/rectilinear.rs:194-198), and on anything else
     // the kernels keep the plain bisection. Per axis: reciprocal cell widths (f64: exact_div's divisor table) and
     // a bucket table lut[k] = partition_point(g < g0 + k*(g_last-g0)/nb), stored as ints in the same blob.
-    bool sorted = true, widths_ok = sizeof(T) == 8;
+    bool sorted = true, widths_ok = true;  // every cell width within the guarded range of the division-free sequences
     for (size_t d = 0; d < ngrids && sorted; ++d) {
         for (size_t i = 0; i < grid_lens[d]; ++i) {
             const double v = static_cast<double>(grids[d][i]);
@@ -472,7 +472,7 @@ int rect_new(int method, const T* const* grids, const size_t* grid_lens, size_t 
             if (i && !(grids[d][i] > grids[d][i - 1])) sorted = false;
             if (i) {
                 const double w = static_cast<double>(grids[d][i]) - static_cast<double>(grids[d][i - 1]);
-                if (!(w >= 0x1p-300 && w < 0x1p301)) widths_ok = false;
+                if (sizeof(T) == 8 ? !(w >= 0x1p-300 && w < 0x1p301) : !(w >= 0x1p-60 && w < 0x1p60)) widths_ok = false;
             }
         }
     }

@@ -357,11 +357,10 @@ __device__ __forceinline__ bool nearest_locate(const EvalArgs<T, N>& a, const T*
             T x0, x1;
             origin = rect_cell_locate<T, N>(a, axes, d, x, x0, x1);
             const T e = O::sub(x, x0), h = O::sub(x1, x0);
-            if constexpr (sizeof(T) == 8) {
-                if (a.rect_fast_div) {  // division-free and exact: device_math.cuh nearest_upper
-                    idx += static_cast<I>(origin + (nearest_upper(e, h * 0.5, h * 0x1p-54) ? 1 : 0)) * stride[d];
-                    continue;
-                }
+            if (a.rect_fast_div) {  // division-free and exact: device_math.cuh nearest_upper (f64 and f32 thresholds)
+                const T tau = O::mul(h, sizeof(T) == 8 ? T(0x1p-54) : T(0x1p-25));
+                idx += static_cast<I>(origin + (nearest_upper(e, O::mul(h, T(0.5)), tau) ? 1 : 0)) * stride[d];
+                continue;
             }
             if constexpr (sizeof(T) == 8) dt = exact_div_slow(e, h);  // axes outside the guarded range only: out of line
             else dt = O::div(e, h);

@@ -131,6 +131,30 @@ class Interpolator:
                C.c_void_p(int(stream)))  # fmt: skip
         )
 
+    def eval_cuda_arrays(self, obs, out, stream: int = 0) -> None:
+        """Enqueue `.interp` on any objects that expose ``__cuda_array_interface__`` (CuPy and Numba arrays, torch
+        CUDA tensors, RMM buffers): zero-copy, stream-ordered, no synchronisation. Every array must
+        be a contiguous 1-D array of the interpolator's dtype; `out` must be writable."""
+        want = "<f8" if self.dtype == np.float64 else "<f4"
+
+        def ptr_len(a, what, writable=False):
+            cai = a.__cuda_array_interface__
+            if cai["typestr"] != want or len(cai["shape"]) != 1:
+                raise TypeError(f"{what} must be a 1-D CUDA array of dtype {self.dtype}")
+            st = cai.get("strides")
+            if st is not None and tuple(st) != (self.dtype.itemsize,):
+                raise TypeError(f"{what} must be contiguous")
+            p, readonly = cai["data"]
+            if writable and readonly:
+                raise TypeError(f"{what} must be writable")
+            return int(p), int(cai["shape"][0])
+
+        pl = [ptr_len(o, "obs") for o in obs]
+        op, n = ptr_len(out, "out", writable=True)
+        if any(m != n for _, m in pl):
+            raise AssertionError("Dimension mismatch")
+        self.eval_device([p for p, _ in pl], n, op, stream)
+
     def eval_torch(self, obs, out=None, stream=None):
         """Enqueue `.interp` on torch CUDA tensors on torch's current stream (or `stream`)."""
         import torch

@@ -336,6 +336,16 @@ def test_resident_interpolator_device_path_matches_host_path(ib, oracle):
             interp.status(torch.cuda.current_stream().cuda_stream)
         assert interp.first_bad == 99
         interp.status(torch.cuda.current_stream().cuda_stream)  # cleared
+        # zero-copy through __cuda_array_interface__ (what CuPy / Numba arrays expose; torch tensors do too)
+        dev_obs = [torch.from_numpy(o).cuda() for o in obs]
+        cai_out = torch.full((n,), -1.0, dtype=torch.float64, device="cuda")
+        interp.eval_cuda_arrays(dev_obs, cai_out, torch.cuda.current_stream().cuda_stream)
+        interp.status(torch.cuda.current_stream().cuda_stream)
+        assert_same_bits(cai_out.cpu().numpy(), host)
+        with pytest.raises(TypeError):
+            interp.eval_cuda_arrays([o.float() for o in dev_obs], cai_out)
+        with pytest.raises(AssertionError, match="Dimension mismatch"):
+            interp.eval_cuda_arrays([dev_obs[0][:10], dev_obs[1], dev_obs[2]], cai_out)
     want = oracle.interpn_regular("cubic", w.dims, w.starts, w.steps, vals, obs, nthreads=8)
     assert_same_bits(host, want)
 

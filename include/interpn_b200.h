@@ -185,7 +185,16 @@ typedef struct interpn_b200_interp interpn_b200_interp;
      * default stream) and returns without synchronising. Unrepresentable points are not written; their smallest  \
      * index is latched in the interp and read by interpn_b200_interp_status(). */                                \
     int interpn_b200_interp_eval_device_##SUFFIX(interpn_b200_interp* interp, const T* const* obs, size_t nobs,   \
-                                                 size_t n, T* out, void* stream);
+                                                 size_t n, T* out, void* stream);                                 \
+    /* Several fields over ONE grid and ONE query batch (the pattern of the reference's benchmark, six            \
+     * interpolators on one grid, bench_cpu.py:501-510): `interps` are `nfields` interpolators built over the      \
+     * same grid with the same method (else "Dimension mismatch"), `outs` a host array of `nfields` device         \
+     * pointers. Multilinear and nearest fields on grids within L2 share one cell location per point; every       \
+     * field's result is bit-identical to its own interpn_b200_interp_eval_device_* call. Failures are latched   \
+     * on interps[0]. */                                                                                          \
+    int interpn_b200_interp_eval_fields_device_##SUFFIX(interpn_b200_interp* const* interps, size_t nfields,      \
+                                                        const T* const* obs, size_t nobs, size_t n,               \
+                                                        T* const* outs, void* stream);
 
 INTERPN_B200_DECLARE_INTERP(f64, double)
 INTERPN_B200_DECLARE_INTERP(f32, float)

@@ -205,6 +205,12 @@ struct interpn_b200_interp {
 
 namespace {
 
+unsigned long long fnv1a(unsigned long long h, const void* p, size_t bytes) {
+    const unsigned char* b = static_cast<const unsigned char*>(p);
+    for (size_t i = 0; i < bytes; ++i) h = (h ^ b[i]) * 1099511628211ull;
+    return h;
+}
+
 size_t product(const size_t* d, size_t n) {
     size_t p = 1;
     for (size_t i = 0; i < n; ++i) p *= d[i];
@@ -359,6 +365,8 @@ int regular_new(int method, const size_t* dims, size_t ndims, const T* starts, s
         g.step[d] = static_cast<double>(steps[d]);
     }
     set_strides(g);
+    g.grid_hash = fnv1a(fnv1a(fnv1a(14695981039346656037ull, g.dim, sizeof(int) * ndims), g.start, sizeof(double) * ndims),
+                        g.step, sizeof(double) * ndims);
     st = upload_vals(h, vals, vals_location);
     if (st == INTERPN_B200_OK) st = finish_new(h);
     if (st != INTERPN_B200_OK) {
@@ -460,6 +468,7 @@ int rect_new(int method, const T* const* grids, const size_t* grid_lens, size_t 
         g.axis_off[d] = static_cast<int>(packed.size());
         packed.insert(packed.end(), grids[d], grids[d] + grid_lens[d]);
     }
+    g.grid_hash = fnv1a(fnv1a(14695981039346656037ull, g.dim, sizeof(int) * ngrids), packed.data(), packed.size() * sizeof(T));
     // Search accelerators (kernels.cuh rect_lower_bound), valid only for strictly increasing finite axes — the
     // reference itself checks just the first two nodes (multilinear/rectilinear.rs:194-198), and on anything else
     // the kernels keep the plain bisection. Per axis: reciprocal cell widths (f64: exact_div's divisor table) and
@@ -612,6 +621,45 @@ int eval_device(interpn_b200_interp* h, const T* const* obs, size_t nobs, size_t
     if (n == 0) return INTERPN_B200_OK;
     if (!out) return INTERPN_B200_ERR_INVALID_ARG;
     CUDA_TRY(launch_eval<T>(h->g, obs, n, out, h->first_bad_dev, 0ull, static_cast<cudaStream_t>(stream)));
+    return INTERPN_B200_OK;
+}
+
+// Fused multi-field evaluation (launch_fields.cu): every interpolator of `hs` must have been built
+// over the same grid with the same method; the cell location runs once per point. Unrepresentable points are latched on
+// hs[0] (interpn_b200_interp_status(hs[0], ...)). Combinations without a fused kernel (multicubic, N > 6, grids beyond
+// L2) are evaluated field by field through the ordinary path, so the call is always valid and always bit-identical to
+// `nfields` separate calls.
+template <class T>
+int eval_fields_device(interpn_b200_interp* const* hs, size_t nfields, const T* const* obs, size_t nobs, size_t n,
+                       T* const* outs, void* stream) {
+    if (!hs || !outs || nfields == 0 || (nobs && !obs)) return INTERPN_B200_ERR_INVALID_ARG;
+    for (size_t k = 0; k < nfields; ++k) {
+        if (!hs[k] || (n && !outs[k])) return INTERPN_B200_ERR_INVALID_ARG;
+        if (hs[k]->g.elem != static_cast<int>(sizeof(T))) return INTERPN_B200_ERR_INVALID_ARG;
+    }
+    const DeviceGrid& g0 = hs[0]->g;
+    if (nobs != static_cast<size_t>(g0.ndims)) return INTERPN_B200_ERR_DIM_MISMATCH;
+    for (size_t k = 1; k < nfields; ++k) {
+        const DeviceGrid& g = hs[k]->g;
+        if (g.method != g0.method || g.rect != g0.rect || g.ndims != g0.ndims || g.linearize != g0.linearize ||
+            g.nvals != g0.nvals || g.grid_hash != g0.grid_hash)
+            return INTERPN_B200_ERR_DIM_MISMATCH;  // not the same grid
+    }
+    if (n == 0) return INTERPN_B200_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    for (size_t k0 = 0; k0 < nfields; k0 += kMaxFields) {
+        const int nf = static_cast<int>(nfields - k0 < static_cast<size_t>(kMaxFields) ? nfields - k0 : kMaxFields);
+        const DeviceGrid* grids[kMaxFields];
+        for (int k = 0; k < nf; ++k) grids[k] = &hs[k0 + k]->g;
+        cudaError_t e = launch_eval_fields<T>(grids, nf, obs, n, outs + k0, hs[0]->first_bad_dev, s);
+        if (e == cudaErrorNotSupported) {
+            cudaGetLastError();
+            for (int k = 0; k < nf; ++k)
+                CUDA_TRY(launch_eval<T>(hs[k0 + k]->g, obs, n, outs[k0 + k], hs[0]->first_bad_dev, 0ull, s));
+        } else {
+            CUDA_TRY(e);
+        }
+    }
     return INTERPN_B200_OK;
 }
 
@@ -933,6 +981,11 @@ int interpn_b200_sm_count(void) {
     int interpn_b200_interp_eval_device_##SUFFIX(interpn_b200_interp* interp, const T* const* obs, size_t nobs,        \
                                                  size_t n, T* out, void* stream) {                                     \
         return eval_device<T>(interp, obs, nobs, n, out, stream);                                                      \
+    }                                                                                                                  \
+    int interpn_b200_interp_eval_fields_device_##SUFFIX(interpn_b200_interp* const* interps, size_t nfields,           \
+                                                        const T* const* obs, size_t nobs, size_t n, T* const* outs,    \
+                                                        void* stream) {                                                \
+        return eval_fields_device<T>(interps, nfields, obs, nobs, n, outs, stream);                                    \
     }
 
 INTERPN_B200_DEFINE(f64, double)

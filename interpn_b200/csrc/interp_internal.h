@@ -49,6 +49,7 @@ struct DeviceGrid {
     int rect_cubic_table = 0;       // cubic, strictly increasing finite axes: per-cell constant table present
     int ct_off[kMaxNd] = {};        // element offset of axis d's cubic cell table (dim+1 rows of 12 elements, 16-byte aligned)
     int sm_count = 148;
+    unsigned long long grid_hash = 0;  // FNV-1a of dims and starts/steps or axes: two interpolators over the same grid agree
 };
 
 // Enqueue one evaluation of `n` query points. `obs` is a HOST array of ndims device pointers.
@@ -56,6 +57,13 @@ struct DeviceGrid {
 template <class T>
 cudaError_t launch_eval(const DeviceGrid& g, const T* const* obs, size_t n, T* out,
                         unsigned long long* first_bad, unsigned long long index_base, cudaStream_t stream);
+
+// Fused evaluation of up to kMaxFields fields over one grid and one query batch (launch_fields.cu). Returns
+// cudaErrorNotSupported when there is no fused kernel for the combination.
+constexpr int kMaxFields = 8;
+template <class T>
+cudaError_t launch_eval_fields(const DeviceGrid* const* grids, int nf, const T* const* obs, size_t n, T* const* outs,
+                               unsigned long long* first_bad, cudaStream_t stream);
 
 // one_dim kernels (device pointers). kind: INTERPN_B200_1D_*; rect: grid != nullptr.
 template <class T>

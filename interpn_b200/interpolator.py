@@ -131,6 +131,44 @@ class Interpolator:
                C.c_void_p(int(stream)))  # fmt: skip
         )
 
+    @staticmethod
+    def eval_fields_device(interps: Sequence["Interpolator"], obs_ptrs: Sequence[int], n: int, out_ptrs: Sequence[int],
+                           stream: int = 0) -> None:
+        """Several fields over one grid and one query batch: `interps` were built over the same grid
+        with the same method, `out_ptrs[k]` receives field k. Multilinear and nearest fields on grids within L2 share
+        one cell location per point; results equal `len(interps)` separate `eval_device` calls bit for bit. Failures
+        are latched on `interps[0]` (`interps[0].status(stream)`)."""
+        first = interps[0]
+        if any(i._sfx != first._sfx for i in interps) or len(out_ptrs) != len(interps):
+            raise AssertionError("Dimension mismatch")
+        ct = first._ct
+        hs = (C.c_void_p * len(interps))(*[i._h for i in interps])
+        k = len(obs_ptrs)
+        optrs = (C.POINTER(ct) * max(k, 1))()
+        for i, p in enumerate(obs_ptrs):
+            optrs[i] = C.cast(C.c_void_p(int(p)), C.POINTER(ct))
+        outs = (C.POINTER(ct) * len(interps))()
+        for i, p in enumerate(out_ptrs):
+            outs[i] = C.cast(C.c_void_p(int(p)), C.POINTER(ct))
+        fn = getattr(lib, f"interpn_b200_interp_eval_fields_device_{first._sfx}")
+        _lib.check(fn(hs, C.c_size_t(len(interps)), optrs, C.c_size_t(k), C.c_size_t(int(n)), outs, C.c_void_p(int(stream))))
+
+    @staticmethod
+    def eval_fields_torch(interps: Sequence["Interpolator"], obs, outs=None, stream=None):
+        """`eval_fields_device` on torch CUDA tensors (torch's current stream unless `stream` is given)."""
+        import torch
+
+        n = obs[0].numel() if len(obs) else 0
+        want = torch.float64 if interps[0].dtype == np.float64 else torch.float32
+        for o in obs:
+            if not (o.is_cuda and o.dtype == want and o.is_contiguous() and o.dim() == 1 and o.numel() == n):
+                raise TypeError("obs must be contiguous 1-D CUDA tensors of the interpolators' dtype and one length")
+        if outs is None:
+            outs = [torch.empty(n, dtype=want, device=obs[0].device) for _ in interps]
+        s = stream if stream is not None else torch.cuda.current_stream(obs[0].device)
+        Interpolator.eval_fields_device(interps, [o.data_ptr() for o in obs], n, [o.data_ptr() for o in outs], s.cuda_stream)
+        return outs
+
     def eval_cuda_arrays(self, obs, out, stream: int = 0) -> None:
         """Enqueue `.interp` on any objects that expose ``__cuda_array_interface__`` (CuPy and Numba arrays, torch
         CUDA tensors, RMM buffers): zero-copy, stream-ordered, no synchronisation. Every array must

@@ -350,6 +350,53 @@ def test_resident_interpolator_device_path_matches_host_path(ib, oracle):
     assert_same_bits(host, want)
 
 
+@pytest.mark.parametrize("method,ndims,rect", [("linear", 3, False), ("linear", 4, True), ("linear", 1, False), ("linear", 7, False),
+                                               ("nearest", 3, False), ("nearest", 2, True), ("cubic", 3, False), ("cubic", 2, True)])
+def test_fused_fields_equal_separate_calls(ib, oracle, method, ndims, rect):
+    """Several fields over one grid and one query batch: one cell location per point for multilinear
+    and nearest, field by field for the rest — either way every field equals its own evaluation (and the oracle) bit for
+    bit, including ten fields (more than one fused launch holds) and the refusal of a different grid."""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(31 + ndims)
+    n = 30000
+    max_dim = {1: 40, 2: 20, 3: 12, 4: 8, 7: 4}[ndims]
+    dims, grids, starts, steps, vals, obs = random_case(rng, ndims, n, 4, max_dim, np.float64)
+    nf = 10 if method == "nearest" else 3
+    fields = [rng.standard_normal(vals.size) for _ in range(nf)]
+    def make(v, g=grids, d=dims):
+        if rect:
+            return ib.Interpolator.rectilinear(method, g, v, True)
+        return ib.Interpolator.regular(method, d, starts, steps, v, True)
+    interps = [make(v) for v in fields]
+    dev_obs = [torch.from_numpy(o).cuda() for o in obs]
+    outs = ib.Interpolator.eval_fields_torch(interps, dev_obs)
+    interps[0].status(torch.cuda.current_stream().cuda_stream)
+    for k, v in enumerate(fields):
+        if rect:
+            want = oracle.interpn_rectilinear(method, grids, v, obs, linearize_extrapolation=True, nthreads=4)
+        else:
+            want = oracle.interpn_regular(method, dims, starts, steps, v, obs, linearize_extrapolation=True, nthreads=4)
+        assert_same_bits(outs[k].cpu().numpy(), want, f"field {k}")
+        assert_same_bits(interps[k].eval(obs), want, f"field {k} alone")
+    # a point no regular grid can represent is latched on the first interpolator
+    if not rect:
+        dev_obs[0][123] = float("nan")
+        ib.Interpolator.eval_fields_torch(interps, dev_obs, outs)
+        with pytest.raises(AssertionError, match="Unrepresentable coordinate value"):
+            interps[0].status(torch.cuda.current_stream().cuda_stream)
+        assert interps[0].first_bad == 123
+    # another grid is refused
+    other_grids = [g * 1.5 for g in grids]
+    if rect:
+        other = ib.Interpolator.rectilinear(method, other_grids, fields[0], True)
+    else:
+        other = ib.Interpolator.regular(method, dims, starts, steps * 2.0, fields[0], True)
+    with pytest.raises(AssertionError, match="Dimension mismatch"):
+        ib.Interpolator.eval_fields_torch([interps[0], other], dev_obs)
+    for it in interps + [other]:
+        it.close()
+
+
 def test_vals_from_device_and_uninitialised_storage(ib):
     torch = pytest.importorskip("torch")
     rng = np.random.default_rng(8)

@@ -286,16 +286,18 @@ __device__ __forceinline__ bool quad4_locate(const EvalArgs<T, N>& a, const T*, 
         int f = 0;
         T t = T(0);
         bool good = false;
-        if constexpr (sizeof(T) == 8) {
-            const double dd = __dsub_rn(x[d], a.start[d]);
-            f = __double2int_rd(__dmul_rn(dd, a.rstep[d]));
-            const double r = __fma_rn(-__int2double_rn(f), a.step[d], dd);
+        {
+            // |f| bound of the remainder proof: 2^30 in f64, 2^12 in f32 (device_math.cuh, the f32 twins)
+            constexpr unsigned kSane = sizeof(T) == 8 ? (1u << 30) : (1u << 12);
+            const T dd = O::sub(x[d], a.start[d]);
+            f = O::floor_sat(O::mul(dd, a.rstep[d]));
+            const T r = O::fma(-O::from_int(f), a.step[d], dd);
             const int origin = min(max(f, 1) - 1, dim - 4);
-            const double x1 = __dadd_rn(a.start[d], __dmul_rn(a.step[d], __int2double_rn(origin + 1)));
-            const double e = __dsub_rn(x[d], x1);
+            const T x1 = O::add(a.start[d], O::mul(a.step[d], O::from_int(origin + 1)));
+            const T e = O::sub(x[d], x1);
             t = markstein_div(e, a.step[d], a.rstep[d]);
-            good = a.fast_div != 0 && r >= 0.0 && r <= a.lim[d] && static_cast<unsigned>(f) + (1u << 30) <= (1u << 31) &&
-                   markstein_operand_ok(e);
+            good = a.fast_div != 0 && r >= T(0) && r <= static_cast<T>(a.lim[d]) &&
+                   static_cast<unsigned>(f) + kSane <= 2u * kSane && markstein_operand_ok(e);
         }
         if (!good) {
             const Quad4Exact<T> ex = quad4_locate_exact<T>(x[d], a.start[d], a.step[d], a.rstep[d], a.fast_div != 0, dim);

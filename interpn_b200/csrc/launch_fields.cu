@@ -17,21 +17,65 @@ struct FieldArgs {
     int nf;
 };
 
-template <class T, int N, bool RECT, int WL>
+// Both kernels follow their single-field twins (kernels.cuh linear_kernel / nearest_kernel): a thread owns P consecutive
+// points — one vector load per coordinate array, P independent locate chains — and then walks the fields, P gathers /
+// lerp trees in flight per field and one vector store per field. The n % P tail is evaluated one point per thread.
+template <class T, int N, bool RECT, int WL, int P>
 __global__ void __launch_bounds__(kBlock) linear_fields_kernel(const __grid_constant__ EvalArgs<T, N> a,
                                                                const __grid_constant__ FieldArgs<T> f) {
     const int(&stride)[N] = a.istride;
     const T* axes = nullptr;
     if constexpr (RECT) axes = stage_axes<T, N>(a);
     const unsigned long long gstride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
-    for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n; i += gstride) {
+    const unsigned long long gtid = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const unsigned long long ngroups = a.n / P;
+    for (unsigned long long g = gtid; g < ngroups; g += gstride) {
+        const unsigned long long i0 = g * P;
+        T xs[P][N];
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+            T v[P];
+            load_query_vec<T, P>(a.obs[d] + i0, v);
+#pragma unroll
+            for (int p = 0; p < P; ++p) xs[p][d] = v[p];
+        }
+        T t[P][N];
+        int base[P];
+        bool ok[P];
+        bool all_ok = true;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            ok[p] = linear_locate_any<T, N, RECT, int, (WL != 0)>(a, axes, xs[p], t[p], base[p]);
+            all_ok = all_ok && ok[p];
+            if (!ok[p]) base[p] = 0;  // keep the gathers in range; the values are discarded
+        }
+#pragma unroll 1
+        for (int k = 0; k < f.nf; ++k) {
+            T res[P];
+#pragma unroll
+            for (int p = 0; p < P; ++p) res[p] = linear_tree<T, N, WL, int>(f.vals[k], f.win[k], base[p], stride, t[p]);
+            if (all_ok) {
+                store_result_vec<T, P>(f.out[k] + i0, res);
+            } else {
+#pragma unroll
+                for (int p = 0; p < P; ++p)
+                    if (ok[p]) store_result(f.out[k] + i0 + p, res[p]);
+            }
+        }
+        if (!all_ok) {
+#pragma unroll
+            for (int p = 0; p < P; ++p)
+                if (!ok[p]) report_bad(a, i0 + p);
+        }
+    }
+    const unsigned long long i = ngroups * P + gtid;
+    if (P > 1 && i < a.n) {
         T xs[N];
 #pragma unroll
         for (int d = 0; d < N; ++d) xs[d] = load_query(a.obs[d] + i);
         T t[N];
         int base;
         if (linear_locate_any<T, N, RECT, int, (WL != 0)>(a, axes, xs, t, base)) {
-#pragma unroll 2
             for (int k = 0; k < f.nf; ++k) store_result(f.out[k] + i, linear_tree<T, N, WL, int>(f.vals[k], f.win[k], base, stride, t));
         } else {
             report_bad(a, i);
@@ -39,19 +83,59 @@ __global__ void __launch_bounds__(kBlock) linear_fields_kernel(const __grid_cons
     }
 }
 
-template <class T, int N, bool RECT>
+template <class T, int N, bool RECT, int P>
 __global__ void __launch_bounds__(kBlock) nearest_fields_kernel(const __grid_constant__ EvalArgs<T, N> a,
                                                                 const __grid_constant__ FieldArgs<T> f) {
     const T* axes = nullptr;
     if constexpr (RECT) axes = stage_axes<T, N>(a);
     const unsigned long long gstride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
-    for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n; i += gstride) {
+    const unsigned long long gtid = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const unsigned long long ngroups = a.n / P;
+    for (unsigned long long g = gtid; g < ngroups; g += gstride) {
+        const unsigned long long i0 = g * P;
+        T xs[P][N];
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+            T v[P];
+            load_query_vec<T, P>(a.obs[d] + i0, v);
+#pragma unroll
+            for (int p = 0; p < P; ++p) xs[p][d] = v[p];
+        }
+        int idx[P];
+        bool ok[P];
+        bool all_ok = true;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            ok[p] = nearest_locate_any<T, N, RECT, int>(a, axes, xs[p], idx[p]);
+            all_ok = all_ok && ok[p];
+            if (!ok[p]) idx[p] = 0;
+        }
+#pragma unroll 2
+        for (int k = 0; k < f.nf; ++k) {
+            T res[P];
+#pragma unroll
+            for (int p = 0; p < P; ++p) res[p] = __ldg(f.vals[k] + idx[p]);
+            if (all_ok) {
+                store_result_vec<T, P>(f.out[k] + i0, res);
+            } else {
+#pragma unroll
+                for (int p = 0; p < P; ++p)
+                    if (ok[p]) store_result(f.out[k] + i0 + p, res[p]);
+            }
+        }
+        if (!all_ok) {
+#pragma unroll
+            for (int p = 0; p < P; ++p)
+                if (!ok[p]) report_bad(a, i0 + p);
+        }
+    }
+    const unsigned long long i = ngroups * P + gtid;
+    if (P > 1 && i < a.n) {
         T xs[N];
 #pragma unroll
         for (int d = 0; d < N; ++d) xs[d] = load_query(a.obs[d] + i);
         int idx;
         if (nearest_locate_any<T, N, RECT, int>(a, axes, xs, idx)) {
-#pragma unroll 4
             for (int k = 0; k < f.nf; ++k) store_result(f.out[k] + i, __ldg(f.vals[k] + idx));
         } else {
             report_bad(a, i);
@@ -60,7 +144,7 @@ __global__ void __launch_bounds__(kBlock) nearest_fields_kernel(const __grid_con
 }
 
 template <class T, int N, class K>
-static cudaError_t launch_fields_kernel(K kernel, const DeviceGrid& g, const T* const* obs, size_t n, const FieldArgs<T>& f,
+static cudaError_t launch_fields_kernel(K kernel, int P, const DeviceGrid& g, const T* const* obs, size_t n, const FieldArgs<T>& f,
                                         unsigned long long* first_bad, cudaStream_t stream, bool window) {
     EvalArgs<T, N> a = make_args<T, N>(g, obs, n, f.out[0], first_bad, 0ull);
     if (g.rect_cell && g.method == 0 && !window && g.axes_core > 0) {  // as launch_generic: no cell tables without a window
@@ -72,17 +156,42 @@ static cudaError_t launch_fields_kernel(K kernel, const DeviceGrid& g, const T* 
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
     }
-    kernel<<<grid_for(n, g.sm_count, 8), kBlock, smem, stream>>>(a, f);
+    kernel<<<grid_for((n + P - 1) / P, g.sm_count, 8), kBlock, smem, stream>>>(a, f);
     count_launch();
     return cudaGetLastError();
+}
+
+// Points per thread as in the single-field launchers; 1 when a coordinate array or an output is not vector-aligned.
+template <class T>
+static bool fields_aligned(const T* const* obs, int ndims, const FieldArgs<T>& f, int P) {
+    const uintptr_t mask = static_cast<uintptr_t>(P) * sizeof(T) - 1;
+    uintptr_t bits = 0;
+    for (int d = 0; d < ndims; ++d) bits |= reinterpret_cast<uintptr_t>(obs[d]);
+    for (int k = 0; k < f.nf; ++k) bits |= reinterpret_cast<uintptr_t>(f.out[k]);
+    return (bits & mask) == 0;
 }
 
 template <class T, int N, bool RECT>
 static cudaError_t linear_fields_n(const DeviceGrid& g, const T* const* obs, size_t n, const FieldArgs<T>& f,
                                    unsigned long long* first_bad, cudaStream_t stream, bool window) {
     constexpr int WLW = N >= 2 ? 4 : 2;
-    if (window) return launch_fields_kernel<T, N>(linear_fields_kernel<T, N, RECT, WLW>, g, obs, n, f, first_bad, stream, true);
-    return launch_fields_kernel<T, N>(linear_fields_kernel<T, N, RECT, 0>, g, obs, n, f, first_bad, stream, false);
+    constexpr int P = linear_points_per_thread<N>();
+    const bool vec = P > 1 && n >= static_cast<size_t>(P) && fields_aligned<T>(obs, N, f, P);
+    if (window) {
+        if (vec) return launch_fields_kernel<T, N>(linear_fields_kernel<T, N, RECT, WLW, P>, P, g, obs, n, f, first_bad, stream, true);
+        return launch_fields_kernel<T, N>(linear_fields_kernel<T, N, RECT, WLW, 1>, 1, g, obs, n, f, first_bad, stream, true);
+    }
+    if (vec) return launch_fields_kernel<T, N>(linear_fields_kernel<T, N, RECT, 0, P>, P, g, obs, n, f, first_bad, stream, false);
+    return launch_fields_kernel<T, N>(linear_fields_kernel<T, N, RECT, 0, 1>, 1, g, obs, n, f, first_bad, stream, false);
+}
+
+template <class T, int N, bool RECT>
+static cudaError_t nearest_fields_n(const DeviceGrid& g, const T* const* obs, size_t n, const FieldArgs<T>& f,
+                                    unsigned long long* first_bad, cudaStream_t stream) {
+    constexpr int P = (RECT && sizeof(T) == 8) ? IB200_P_NEAREST_RECT : IB200_P_NEAREST;
+    const bool vec = n >= static_cast<size_t>(P) && fields_aligned<T>(obs, N, f, P);
+    if (vec) return launch_fields_kernel<T, N>(nearest_fields_kernel<T, N, RECT, P>, P, g, obs, n, f, first_bad, stream, true);
+    return launch_fields_kernel<T, N>(nearest_fields_kernel<T, N, RECT, 1>, 1, g, obs, n, f, first_bad, stream, true);
 }
 
 // grids[k] all describe the same grid (checked by the caller); nf <= kMaxFields. Returns cudaErrorNotSupported when
@@ -105,7 +214,12 @@ cudaError_t launch_eval_fields(const DeviceGrid* const* grids, int nf, const T* 
         window = window && grids[k]->win != nullptr && grids[k]->win_width == patch &&
                  g.nvals * sizeof(T) * static_cast<size_t>(patch) <= kWindowL2Bytes;
     }
-    if (g.method == 0 && !window && g.nvals * sizeof(T) > (size_t(96) << 20)) return cudaErrorNotSupported;  // bin-swept territory
+    // Fusing multiplies the gathered working set by the number of fields: it pays while all of them sit in L2 together
+    // (measured, six fields: 3-D nearest 128^3 — 6 x 16 MB — 126 fused vs 160 G field-points/s field by field, the
+    // patch copies of 100^3 — 6 x 32 MB — 69 vs 101; a rectilinear search shared six ways still wins, 127 vs 98).
+    const size_t gathered = g.nvals * sizeof(T) * static_cast<size_t>(window ? patch : 1);
+    const size_t budget = (g.method == 2 && g.rect) ? (size_t(128) << 20) : (size_t(40) << 20);
+    if (gathered * static_cast<size_t>(nf) > budget) return cudaErrorNotSupported;
     cudaError_t err = cudaErrorNotSupported;
     if (g.method == 0) {
         if (g.rect) {
@@ -115,9 +229,9 @@ cudaError_t launch_eval_fields(const DeviceGrid* const* grids, int nf, const T* 
         }
     } else {
         if (g.rect) {
-            IB200_SWITCH_N(6, err = (launch_fields_kernel<T, N>(nearest_fields_kernel<T, N, true>, g, obs, n, f, first_bad, stream, true));)
+            IB200_SWITCH_N(6, err = (nearest_fields_n<T, N, true>(g, obs, n, f, first_bad, stream));)
         } else {
-            IB200_SWITCH_N(6, err = (launch_fields_kernel<T, N>(nearest_fields_kernel<T, N, false>, g, obs, n, f, first_bad, stream, true));)
+            IB200_SWITCH_N(6, err = (nearest_fields_n<T, N, false>(g, obs, n, f, first_bad, stream));)
         }
     }
     return err;

@@ -15,9 +15,18 @@ from interpn_b200 import workloads as W
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 6
 dev = torch.device("cuda", 0)
 res = []
-for name, n in (("x_linear3d_reg100", 50_000_000), ("x_linear4d_rect32", 50_000_000), ("c5_nearest3d_reg128", 50_000_000),
-                ("c5_nearest3d_rect128", 50_000_000), ("c1_linear3d_reg20", 50_000_000)):
-    w = W.get(name)
+def small(name, method, ndims, size, rect):
+    """A grid small enough that K of its gathered copies sit in L2 together."""
+    if rect:
+        return W._rectilinear(name, method, ndims, size, np.float64, 100_000_000, oob_fraction=0.05)
+    return W._regular(name, method, [size] * ndims, [0.0] * ndims, [1.0] * ndims, np.float64, 100_000_000, oob_fraction=0.05)
+
+
+CASES = [(W.get("x_linear3d_reg100"), 50_000_000), (W.get("c5_nearest3d_reg128"), 50_000_000), (W.get("c5_nearest3d_rect128"), 50_000_000),
+         (small("linear3d_reg48", "linear", 3, 48, False), 50_000_000), (small("linear4d_rect16", "linear", 4, 16, True), 50_000_000),
+         (small("nearest3d_reg64", "nearest", 3, 64, False), 50_000_000), (small("nearest2d_rect512", "nearest", 2, 512, True), 50_000_000)]
+for w, n in CASES:
+    name = w.name
     obs = w.queries(0, n, "torch", dev)
     rng = np.random.default_rng(1)
     interps = []

@@ -22,7 +22,13 @@
 #pragma once
 #include "kernels.cuh"
 
+#ifndef IB200_QUAD4_UNROLLK
+#define IB200_QUAD4_UNROLLK 1
+#endif
+
 namespace ib200 {
+
+constexpr int kQuad4UnrollK = IB200_QUAD4_UNROLLK;  // outer row loop of a 4-D footprint (quad4_rows): 1 = rolled
 
 // Per-dimension parameters of a 1-D step.
 template <class T, bool RECT>
@@ -367,7 +373,7 @@ __device__ __forceinline__ void quad4_rows(const EvalArgs<T, N>& a, const T* __r
         if constexpr (D >= 2) {
             // Not unrolled (code size: a 4-D footprint unrolled 16 ways did not fit the instruction cache). The four
             // partial rows are shifted through `sub` so that no register array is indexed dynamically.
-#pragma unroll 1
+#pragma unroll(kQuad4UnrollK)
             for (int k = 0; k < 4; ++k) {
                 T rk[4];
                 quad4_rows<D - 1, T, N, RECT>(a, axes, idx + cubic_perm_k(mode, k) * stride, sp, flags, none_mask, rk);

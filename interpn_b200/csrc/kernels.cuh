@@ -8,6 +8,8 @@
 // element per thread per array; vals = flat C-order in HBM/L2; rectilinear axes packed back to
 // back and staged once per CTA into shared memory when they fit.
 #pragma once
+#include <type_traits>
+
 #include "device_math.cuh"
 
 namespace ib200 {
@@ -41,6 +43,7 @@ struct EvalArgs {
     int linearize;
     unsigned long long* first_bad;
     unsigned long long index_base;
+    int slab_lo, slab_hi;  // slab passes (linear_slab_kernel): cells [slab_lo, slab_hi) of dimension 0; hi < 0 = to the end
     const unsigned* remap;  // bin-swept evaluation: original (chunk-local) index of point i, else nullptr
     unsigned long long* work;  // bin-swept evaluation: zeroed counter for dynamic block scheduling, else nullptr
 };
@@ -189,6 +192,23 @@ __device__ __forceinline__ void load_row(const T* __restrict__ vals, const T* __
     }
 }
 
+// A row of two values straight from `vals` as ONE aligned pair load plus, for odd flat indices only, a predicated
+// scalar load: on average 1.5 L1 wavefronts per lane instead of the 2 of two scalar loads (the slab-pass kernel sits
+// on the L1 wavefront rate: l1tex 85 %, profiles/r1_p6_c3l_slab_ncu.json). `vals` is the library's own allocation
+// (256-byte aligned), and the pair that contains idx never reaches past idx + 1.
+template <class T, class I>
+__device__ __forceinline__ void load_row_aligned(const T* __restrict__ vals, I idx, T (&r)[2]) {
+    using V = typename std::conditional<sizeof(T) == 8, double2, float2>::type;
+    const V q = __ldg(reinterpret_cast<const V*>(vals) + (idx >> 1));
+    if (idx & 1) {
+        r[0] = q.y;
+        r[1] = __ldg(vals + idx + 1);
+    } else {
+        r[0] = q.x;
+        r[1] = q.y;
+    }
+}
+
 // Query coordinates and results are touched exactly once: streaming loads/stores (evict-first) keep
 // them from displacing the grid in L1/L2.
 template <class T>
@@ -237,16 +257,17 @@ __device__ __forceinline__ void store_result_vec(T* p, const T (&v)[P]) {
 // Reduces dimensions 0..D-1 of the sub-block at flat index `idx` for both positions of the last
 // (contiguous) dimension at once. Each lerp is the reference's `y0 + t*(y1 - y0)` with dimension 0
 // innermost, so every output is bit-identical to the reference's tree; only the load schedule differs.
-template <int D, class T, int N, bool WIN, class I>
+template <int D, class T, int N, bool WIN, class I, bool AL = false>
 __device__ __forceinline__ void linear_rows(const T* __restrict__ vals, const T* __restrict__ win, I idx,
                                             const I (&stride)[N], const T (&t)[N], T (&out)[2]) {
     using O = Ops<T>;
     if constexpr (D == 0) {
-        load_row<T, 2, WIN, I>(vals, win, idx, out);
+        if constexpr (AL) load_row_aligned<T, I>(vals, idx, out);
+        else load_row<T, 2, WIN, I>(vals, win, idx, out);
     } else {
         T lo[2], hi[2];
-        linear_rows<D - 1, T, N, WIN, I>(vals, win, idx, stride, t, lo);
-        linear_rows<D - 1, T, N, WIN, I>(vals, win, idx + stride[D - 1], stride, t, hi);
+        linear_rows<D - 1, T, N, WIN, I, AL>(vals, win, idx, stride, t, lo);
+        linear_rows<D - 1, T, N, WIN, I, AL>(vals, win, idx + stride[D - 1], stride, t, hi);
 #pragma unroll
         for (int j = 0; j < 2; ++j) out[j] = muladd(t[D - 1], O::sub(hi[j], lo[j]), lo[j]);
     }
@@ -272,13 +293,13 @@ __device__ __forceinline__ void linear_patches(const T* __restrict__ win, I idx,
     }
 }
 
-// The whole lerp tree of one located point. WL = layout gathered from: 0 the grid itself, 2 the row-pair window copy,
-// 4 the 2x2 patch copy.
+// The whole lerp tree of one located point. WL = layout gathered from: 0 the grid itself (1: the same through
+// load_row_aligned), 2 the row-pair window copy, 4 the 2x2 patch copy.
 template <class T, int N, int WL, class I>
 __device__ __forceinline__ T linear_tree(const T* __restrict__ vals, const T* __restrict__ win, I base,
                                          const I (&stride)[N], const T (&t)[N]) {
     using O = Ops<T>;
-    constexpr bool WIN = WL != 0;
+    constexpr bool WIN = WL >= 2;
     if constexpr (WL == 4) {
         static_assert(N >= 2, "the patch layout needs two dimensions");
         T v[4];
@@ -288,7 +309,7 @@ __device__ __forceinline__ T linear_tree(const T* __restrict__ vals, const T* __
         return muladd(t[N - 1], O::sub(r1, r0), r0);
     } else {
         T r[2];
-        linear_rows<N - 1, T, N, WIN, I>(vals, win, base, stride, t, r);
+        linear_rows<N - 1, T, N, WIN, I, WL == 1>(vals, win, base, stride, t, r);
         return muladd(t[N - 1], O::sub(r[1], r[0]), r[0]);
     }
 }
@@ -499,6 +520,82 @@ __global__ void __launch_bounds__(kBlock) linear_kernel(const __grid_constant__ 
                 report_bad(a, i);
             }
         }
+    }
+}
+
+// Slab passes — multilinear straight from `vals` on a grid a little beyond L2 (C3: 134 MB against 126 MB), whose
+// footprints are too few rows for the bin-swept path to pay. The batch is evaluated in a few launches; each takes only
+// the points whose dimension-0 coordinate lies between two nodes of axis 0, so that all of a launch's gathers fall in
+// one slab of `vals` that IS L2-resident (every footprint row is otherwise a 32-byte DRAM sector fetch, 417 B/point
+// against 41 algorithmic: profiles/r1_p2_c3_linear4d_rect64_ncu.json).
+// Skipping inside a warp would save nothing (the lanes that skip wait for the ones that gather), so each warp first
+// sifts a tile of kSlabTile points — one coalesced load of coordinate 0 and two compares per point — into a dense list
+// in shared memory, then evaluates the list 32 points at a time with the ordinary locate + lerp tree.
+// The sift only has to PARTITION the batch among the launches (every x belongs to exactly one: e_lo < x <= e_hi, the
+// first launch also takes x <= e_lo and NaN, the last everything above); which cell the point really falls in is
+// decided by the ordinary locate, so results and error reports are those of linear_kernel bit for bit.
+#ifndef IB200_SLAB_TILE
+#define IB200_SLAB_TILE 256
+#endif
+constexpr int kSlabTile = IB200_SLAB_TILE;
+#ifndef IB200_SLAB_ROWS
+#define IB200_SLAB_ROWS 0  // 0: two scalar loads per row, 1: load_row_aligned (measured 3 % slower on C3-linear)
+#endif
+#ifndef IB200_SLAB_MINB
+#define IB200_SLAB_MINB 4
+#endif
+template <class T, int N, bool RECT, class I>
+__global__ void __launch_bounds__(kBlock, IB200_SLAB_MINB) linear_slab_kernel(const __grid_constant__ EvalArgs<T, N> a) {
+    using O = Ops<T>;
+    const I(&stride)[N] = strides_of<I>(a);
+    const T* axes = nullptr;
+    if constexpr (RECT) axes = stage_axes<T, N>(a);
+    __shared__ unsigned short s_list[kBlock / 32][kSlabTile];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool first = a.slab_lo == 0, last = a.slab_hi < 0;
+    T e_lo, e_hi;
+    if constexpr (RECT) {
+        e_lo = axes[a.axis_off[0] + a.slab_lo];
+        e_hi = axes[a.axis_off[0] + (last ? 0 : a.slab_hi)];
+    } else {
+        e_lo = O::add(a.start[0], O::mul(a.step[0], O::from_int(a.slab_lo)));
+        e_hi = O::add(a.start[0], O::mul(a.step[0], O::from_int(last ? 0 : a.slab_hi)));
+    }
+    unsigned short* list = s_list[warp];
+    const unsigned long long ntiles = (a.n + kSlabTile - 1) / kSlabTile;
+    const unsigned long long nwarps = static_cast<unsigned long long>(gridDim.x) * (kBlock / 32);
+    for (unsigned long long tile = static_cast<unsigned long long>(blockIdx.x) * (kBlock / 32) + warp; tile < ntiles; tile += nwarps) {
+        const unsigned long long i0 = tile * kSlabTile;
+        const T* x0 = a.obs[0] + i0;
+        const int m = static_cast<int>(min(static_cast<unsigned long long>(kSlabTile), a.n - i0));
+        int count = 0;
+#pragma unroll 4
+        for (int k = 0; k < kSlabTile / 32; ++k) {
+            const int j = k * 32 + lane;
+            bool mine = false;
+            if (j < m) {
+                const T x = __ldg(x0 + j);
+                mine = (first || x > e_lo) && (last || !(x > e_hi));
+            }
+            const unsigned ballot = __ballot_sync(0xffffffffu, mine);
+            if (mine) list[count + __popc(ballot & ((1u << lane) - 1u))] = static_cast<unsigned short>(j);
+            count += __popc(ballot);
+        }
+        __syncwarp();
+        for (int q = lane; q < count; q += 32) {
+            const unsigned long long i = i0 + list[q];
+            T xs[N];
+#pragma unroll
+            for (int d = 0; d < N; ++d) xs[d] = load_query(a.obs[d] + i);
+            T t[N];
+            I base;
+            if (linear_locate_any<T, N, RECT, I, false>(a, axes, xs, t, base)) {
+                store_result(a.out + i, linear_tree<T, N, IB200_SLAB_ROWS, I>(a.vals, a.win, base, stride, t));
+            } else {
+                report_bad(a, i);
+            }
+        }
+        __syncwarp();
     }
 }
 

@@ -18,6 +18,8 @@ inline EvalArgs<T, N> make_args(const DeviceGrid& g, const T* const* obs, size_t
     EvalArgs<T, N> a{};
     a.remap = remap;
     a.work = work;
+    a.slab_lo = 0;
+    a.slab_hi = -1;
     for (int d = 0; d < N; ++d) {
         a.obs[d] = obs[d];
         a.stride[d] = g.stride[d];
@@ -104,6 +106,7 @@ constexpr int linear_points_per_thread() {
 }
 
 struct LaunchOpts {
+    int slab_lo = 0, slab_hi = -1;       // slab passes (kernels.cuh linear_slab_kernel)
     int points_per_thread = 1;
     const unsigned* remap = nullptr;     // bin-swept path: original indices of the sorted points
     unsigned long long* work = nullptr;  // bin-swept path: dynamic block scheduling counter
@@ -120,6 +123,8 @@ inline cudaError_t launch_generic(K kernel, const DeviceGrid& g, const T* const*
     if (n == 0) return cudaSuccess;
     const int points_per_thread = o.points_per_thread, threads_per_point = o.threads_per_point, ctas_per_sm = o.ctas_per_sm;
     EvalArgs<T, N> a = make_args<T, N>(g, obs, n, out, first_bad, index_base, o.remap, o.work);
+    a.slab_lo = o.slab_lo;
+    a.slab_hi = o.slab_hi;
     if (g.rect_cell && g.method == 0 && !o.window && g.axes_core > 0) {
         // multilinear straight from `vals` (grid beyond L2, DRAM-bound): bucket search, cell tables neither read nor
         // staged — the shared memory they would take comes out of L1 (C3-linear 14.2 vs 13.5 G points/s)

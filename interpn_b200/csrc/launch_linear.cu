@@ -54,6 +54,31 @@ cudaError_t launch_linear_n(const DeviceGrid& g, const T* const* obs, size_t n, 
     if constexpr (N >= 2 && N <= 4) {
         if (has_rows) return launch_linear_direct<T, N, RECT, 2>(g, obs, n, out, first_bad, index_base, stream, nullptr, nullptr);
     }
+    // Grids a little beyond L2, footprints too small for the bin-swept path to pay (C3-linear): slab passes
+    // (kernels.cuh linear_slab_kernel), each over the cells of dimension 0 whose rows of `vals` make one L2-resident slab.
+    if constexpr (N >= 3 && N <= 5) {
+        const size_t pass_kb = sweep_env("INTERPN_B200_SLAB_PASS_KB", 45 << 10);  // 0 = off
+        const size_t min_kb = sweep_env("INTERPN_B200_SLAB_MIN_KB", 80 << 10);
+        const size_t min_points = sweep_env("INTERPN_B200_SLAB_MIN_POINTS", 1 << 20);
+        const size_t ctas = sweep_env("INTERPN_B200_SLAB_CTAS", 8);
+        const size_t bytes = g.nvals * sizeof(T);
+        if (pass_kb && bytes > (min_kb << 10) && g.nvals < (size_t(1) << 31) && n >= min_points) {
+            const int passes = static_cast<int>((bytes + (pass_kb << 10) - 1) / (pass_kb << 10));
+            const int cells = g.dim[0] - 1;
+            if (passes >= 2 && passes <= 8 && cells >= passes) {
+                for (int p = 0; p < passes; ++p) {
+                    LaunchOpts o;
+                    o.points_per_thread = kSlabTile / 32;
+                    o.ctas_per_sm = static_cast<int>(ctas);
+                    o.slab_lo = static_cast<int>(static_cast<long long>(cells) * p / passes);
+                    o.slab_hi = p + 1 == passes ? -1 : static_cast<int>(static_cast<long long>(cells) * (p + 1) / passes);
+                    cudaError_t e = launch_generic<T, N>(linear_slab_kernel<T, N, RECT, int>, g, obs, n, out, first_bad, index_base, stream, o);
+                    if (e != cudaSuccess) return e;
+                }
+                return cudaSuccess;
+            }
+        }
+    }
     return launch_linear_direct<T, N, RECT, 0>(g, obs, n, out, first_bad, index_base, stream, nullptr, nullptr);
 }
 

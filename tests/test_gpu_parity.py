@@ -162,6 +162,51 @@ def test_bin_swept_evaluation_bit_exact(ib, oracle, monkeypatch, method, ndims, 
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("ndims", [3, 4, 5])
+def test_slab_passes_bit_exact(ib, oracle, monkeypatch, ndims, dtype):
+    """The slab passes of the multilinear kernels (kernels.cuh linear_slab_kernel: grids a little beyond L2, C3-linear)
+    forced onto small grids: several passes, a ragged last tile, points exactly on the pass edges, below and above the
+    grid, and unrepresentable points reported from different passes."""
+    monkeypatch.setenv("INTERPN_B200_WINDOW_MB", "0")
+    monkeypatch.setenv("INTERPN_B200_SLAB_MIN_KB", "0")
+    monkeypatch.setenv("INTERPN_B200_SLAB_MIN_POINTS", "0")
+    rng = np.random.default_rng(991 + ndims)
+    n = 300_007
+    lo, hi = {3: (9, 16), 4: (6, 9), 5: (5, 6)}[ndims]
+    dims, grids, starts, steps, vals, obs = random_case(rng, ndims, n, lo, hi, dtype)
+    obs[0][:64] = np.resize(grids[0], 64)  # exact nodes of axis 0: the pass edges among them
+    obs[0][64:128] = np.resize(starts[0] + steps[0] * np.arange(dims[0], dtype=dtype), 64)
+    sfx = "f64" if dtype == np.float64 else "f32"
+    pass_kb = max(1, -(-vals.nbytes // (3 * 1024)))
+    passes = -(-vals.nbytes // (pass_kb * 1024))
+    assert 2 <= passes <= dims[0] - 1
+    monkeypatch.setenv("INTERPN_B200_SLAB_PASS_KB", str(pass_kb))
+    before = ib.launch_count()
+    out = np.zeros(n, dtype=dtype)
+    getattr(ib.raw, f"interpn_linear_regular_{sfx}")(dims, starts, steps, vals, obs, out)
+    assert_same_bits(out, oracle.interpn_regular("linear", dims, starts, steps, vals, obs, nthreads=8))
+    out = np.zeros(n, dtype=dtype)
+    getattr(ib.raw, f"interpn_linear_rectilinear_{sfx}")(grids, vals, obs, out)
+    assert_same_bits(out, oracle.interpn_rectilinear("linear", grids, vals, obs, nthreads=8))
+    assert ib.launch_count() >= before + 2 * passes, "the slab-pass kernel did not run"
+    bad = [n // 3, n // 3 + 5000, n // 2]
+    obs2 = [o.copy() for o in obs]
+    obs2[0][bad[0]] = np.nan
+    obs2[1][bad[1]] = np.inf
+    obs2[0][bad[2]] = -np.inf
+    out = np.full(n, -7.0, dtype=dtype)
+    with pytest.raises(AssertionError, match="Unrepresentable coordinate value"):
+        getattr(ib.raw, f"interpn_linear_regular_{sfx}")(dims, starts, steps, vals, obs2, out)
+    want = oracle.interpn_regular("linear", dims, starts, steps, vals, [o[: bad[0]] for o in obs], nthreads=8)
+    assert_same_bits(out[: bad[0]], want)
+    assert np.all(out[bad[0] :] == -7.0)
+    # rectilinear grids never fail (NaN and infinities land in the end cells, like slice::partition_point)
+    out = np.zeros(n, dtype=dtype)
+    getattr(ib.raw, f"interpn_linear_rectilinear_{sfx}")(grids, vals, obs2, out)
+    assert_same_bits(out, oracle.interpn_rectilinear("linear", grids, vals, obs2, nthreads=8))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_cubic_four_node_axes(ib, oracle, dtype):
     """Axes with exactly 4 nodes: origin is always 0 and every saturation class is reachable
     (SURVEY.md appendix A)."""
@@ -216,6 +261,7 @@ WORKLOADS = [
     ("c1_linear3d_reg20", np.float64, 200_000),
     ("c2_cubic3d_reg100", np.float64, 200_000),
     ("c3_linear4d_rect64", np.float64, 200_000),
+    ("c3_linear4d_rect64", np.float64, 1_100_003),  # above the slab passes' point threshold
     ("c3_cubic4d_rect64", np.float64, 60_000),
     ("c4_linear6d_reg24", np.float64, 100_000),
     ("c5_nearest2d_reg1024", np.float64, 300_000),

@@ -74,7 +74,8 @@ def measured_peak_hbm():
 
 
 def ncu_traffic(workload: str):
-    """Per-launch DRAM bytes of the dominant kernel from the committed ncu capture, if any."""
+    """DRAM bytes of the dominant kernel per launch (per step, summed over the launches, where a step is several) from the
+    committed ncu capture, if any."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
         with open(p) as f:
@@ -399,7 +400,8 @@ def run_b200(args):
         "frac": achieved / peak,
         "traffic": ncu_traffic(w.name),
         "peak_source": peak_src,
-        "kernel": "dominant evaluation kernel of the step (one launch per step)",
+        "kernel": "dominant evaluation kernel of the step (one launch per step)" if launches <= args.steps
+        else f"all {launches / max(args.steps, 1):g} launches of a step (sort + evaluation of the bin-swept path, or the slab passes): algorithmic bytes per step over the step's device time",
         "algorithmic_bytes_per_launch": abytes,
         "kernel_ms": kernel_ms,
     }

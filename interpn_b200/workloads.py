@@ -256,10 +256,18 @@ def get(name: str, dtype=np.float64) -> Workload:
         return _rectilinear(name, "cubic", 4, 32, dtype, 100_000_000, linearize=False, oob_fraction=0.10)
     if name == "x_linear4d_rect32":
         return _rectilinear(name, "linear", 4, 32, dtype, 100_000_000, oob_fraction=0.10)
+    # Grids a little beyond L2 (134 / 134 / 95 MB in f64): the slab passes of launch_linear.cu on regular grids
+    if name == "x_linear3d_reg256":
+        return _regular(name, "linear", [256] * 3, [0.0] * 3, [1.0] * 3, dtype, 100_000_000, oob_fraction=0.10)
+    if name == "x_linear4d_reg64":
+        return _regular(name, "linear", [64] * 4, [0.0] * 4, [1.0] * 4, dtype, 100_000_000, oob_fraction=0.10)
+    if name == "x_linear5d_reg26":
+        return _regular(name, "linear", [26] * 5, [0.0] * 5, [1.0] * 5, dtype, 100_000_000)
     raise KeyError(name)
 
 
-EXTRA = ["x_linear3d_reg100", "x_linear4d_reg32", "x_cubic4d_reg32", "x_cubic3d_rect100", "x_cubic4d_rect32", "x_linear4d_rect32"]
+EXTRA = ["x_linear3d_reg100", "x_linear4d_reg32", "x_cubic4d_reg32", "x_cubic3d_rect100", "x_cubic4d_rect32", "x_linear4d_rect32",
+         "x_linear3d_reg256", "x_linear4d_reg64", "x_linear5d_reg26"]
 
 ALL = [
     "c1_linear3d_reg20",

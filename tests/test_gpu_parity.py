@@ -262,6 +262,10 @@ WORKLOADS = [
     ("c2_cubic3d_reg100", np.float64, 200_000),
     ("c3_linear4d_rect64", np.float64, 200_000),
     ("c3_linear4d_rect64", np.float64, 1_100_003),  # above the slab passes' point threshold
+    ("x_linear3d_reg256", np.float64, 1_100_003),  # regular grids a little beyond L2: slab passes
+    ("x_linear4d_reg64", np.float64, 1_100_003),
+    ("x_linear5d_reg26", np.float32, 1_100_003),  # 48 MB in f32: the direct kernel; f64 below
+    ("x_linear5d_reg26", np.float64, 1_100_003),
     ("c3_cubic4d_rect64", np.float64, 60_000),
     ("c4_linear6d_reg24", np.float64, 100_000),
     ("c5_nearest2d_reg1024", np.float64, 300_000),

@@ -541,6 +541,9 @@ constexpr int kSlabTile = IB200_SLAB_TILE;
 #ifndef IB200_SLAB_ROWS
 #define IB200_SLAB_ROWS 0  // 0: two scalar loads per row, 1: load_row_aligned (measured 3 % slower on C3-linear)
 #endif
+#ifndef IB200_SLAB_CELL
+#define IB200_SLAB_CELL 1  // rectilinear axes: 1 = cell tables (three shared-memory loads per dimension), 0 = bucket search
+#endif
 #ifndef IB200_SLAB_MINB
 #define IB200_SLAB_MINB 4
 #endif
@@ -589,7 +592,7 @@ __global__ void __launch_bounds__(kBlock, IB200_SLAB_MINB) linear_slab_kernel(co
             for (int d = 0; d < N; ++d) xs[d] = load_query(a.obs[d] + i);
             T t[N];
             I base;
-            if (linear_locate_any<T, N, RECT, I, false>(a, axes, xs, t, base)) {
+            if (linear_locate_any<T, N, RECT, I, IB200_SLAB_CELL != 0>(a, axes, xs, t, base)) {
                 store_result(a.out + i, linear_tree<T, N, IB200_SLAB_ROWS, I>(a.vals, a.win, base, stride, t));
             } else {
                 report_bad(a, i);

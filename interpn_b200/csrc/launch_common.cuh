@@ -112,6 +112,7 @@ struct LaunchOpts {
     unsigned long long* work = nullptr;  // bin-swept path: dynamic block scheduling counter
     int threads_per_point = 1;           // 4 for the quad-cooperative kernels
     bool window = false;                 // the kernel gathers from the window copy, not from vals
+    bool cell_tables = false;            // the kernel locates rectilinear cells through the cell tables although it gathers from vals
     int ctas_per_sm = 8;
     size_t extra_smem = 0;               // dynamic shared memory beyond the staged axes (cubic_quad4.cuh)
 };
@@ -125,7 +126,7 @@ inline cudaError_t launch_generic(K kernel, const DeviceGrid& g, const T* const*
     EvalArgs<T, N> a = make_args<T, N>(g, obs, n, out, first_bad, index_base, o.remap, o.work);
     a.slab_lo = o.slab_lo;
     a.slab_hi = o.slab_hi;
-    if (g.rect_cell && g.method == 0 && !o.window && g.axes_core > 0) {
+    if (g.rect_cell && g.method == 0 && !o.window && !o.cell_tables && g.axes_core > 0) {
         // multilinear straight from `vals` (grid beyond L2, DRAM-bound): bucket search, cell tables neither read nor
         // staged — the shared memory they would take comes out of L1 (C3-linear 14.2 vs 13.5 G points/s)
         a.rect_cell = 0;

@@ -70,6 +70,7 @@ cudaError_t launch_linear_n(const DeviceGrid& g, const T* const* obs, size_t n, 
                     LaunchOpts o;
                     o.points_per_thread = kSlabTile / 32;
                     o.ctas_per_sm = static_cast<int>(ctas);
+                    o.cell_tables = IB200_SLAB_CELL != 0;
                     o.slab_lo = static_cast<int>(static_cast<long long>(cells) * p / passes);
                     o.slab_hi = p + 1 == passes ? -1 : static_cast<int>(static_cast<long long>(cells) * (p + 1) / passes);
                     cudaError_t e = launch_generic<T, N>(linear_slab_kernel<T, N, RECT, int>, g, obs, n, out, first_bad, index_base, stream, o);

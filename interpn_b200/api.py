@@ -15,13 +15,14 @@ only move the query batch over PCIe.
 from __future__ import annotations
 
 import json
+import weakref
 from collections.abc import Sequence
 from functools import reduce
 from typing import Annotated, Any, ClassVar, Literal
 
 import numpy as np
 from numpy.typing import NDArray
-from pydantic import BaseModel, ConfigDict, Field, PrivateAttr, field_serializer, field_validator, model_validator
+from pydantic import BaseModel, ConfigDict, Field, field_serializer, field_validator, model_validator
 
 from . import raw
 from .interpolator import Interpolator
@@ -77,12 +78,24 @@ def _suffix(dtype) -> str:
 # ---------------------------------------------------------------------------------------------
 
 
+# Grid-resident interpolators of the live models, keyed by id(model). The device handle is deliberately NOT part of
+# a model's state: like the reference's six classes, a model stays plain data — picklable, deep-copyable, equal to
+# another model with the same fields — before and after its first evaluation. A copy or an unpickled model simply
+# builds its own resident interpolator on first use; the entry is closed when its model is collected.
+_RESIDENT: dict[int, Interpolator] = {}
+
+
+def _drop_resident(key: int) -> None:
+    it = _RESIDENT.pop(key, None)
+    if it is not None:
+        it.close()
+
+
 class _Model(BaseModel):
     model_config = ConfigDict(frozen=True, extra="forbid", arbitrary_types_allowed=True)
 
     _method: ClassVar[str] = "linear"
     _max_dims: ClassVar[int] = 8
-    _resident: Interpolator | None = PrivateAttr(default=None)
 
     vals: Array
 
@@ -93,9 +106,12 @@ class _Model(BaseModel):
         raise NotImplementedError
 
     def _interp(self) -> Interpolator:
-        if self._resident is None:
-            self._resident = self._build()
-        return self._resident
+        key = id(self)
+        it = _RESIDENT.get(key)
+        if it is None:
+            it = _RESIDENT[key] = self._build()
+            weakref.finalize(self, _drop_resident, key)
+        return it
 
     def eval(self, obs: list[NDArray], out: NDArray | None = None) -> NDArray:
         """Evaluate at the observation points (``obs`` = [x, y, ...] coordinate arrays), optionally

@@ -78,6 +78,12 @@ cudaError_t launch_check_bounds(const T* x, size_t n, T lo, T hi, T atol, int* f
 // Fills g.win from g.vals (stream-ordered).
 cudaError_t launch_build_window(const DeviceGrid& g, cudaStream_t stream);
 
+// True when the kernels must index `vals` with 64-bit arithmetic (ref: lib.rs:119-144 indexes with usize): grids of
+// 2^31 values or more, or any grid while INTERPN_B200_INDEX64=1 (test hook: runs the `long long` instantiations on
+// small grids; read at every call).
+bool force_index64();
+inline bool index64(const DeviceGrid& g) { return g.nvals >= (size_t(1) << 31) || force_index64(); }
+
 void count_launch();
 void count_swept_launch();
 

@@ -23,7 +23,7 @@ inline EvalArgs<T, N> make_args(const DeviceGrid& g, const T* const* obs, size_t
     for (int d = 0; d < N; ++d) {
         a.obs[d] = obs[d];
         a.stride[d] = g.stride[d];
-        a.istride[d] = g.nvals < (size_t(1) << 31) ? static_cast<int>(g.stride[d]) : 0;
+        a.istride[d] = g.nvals < (size_t(1) << 31) ? static_cast<int>(g.stride[d]) : 0;  // unused by the 64-bit kernels
         a.dim[d] = g.dim[d];
         a.start[d] = static_cast<T>(g.start[d]);
         a.step[d] = static_cast<T>(g.step[d]);

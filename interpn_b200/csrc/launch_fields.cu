@@ -201,7 +201,7 @@ cudaError_t launch_eval_fields(const DeviceGrid* const* grids, int nf, const T* 
                                unsigned long long* first_bad, cudaStream_t stream) {
     const DeviceGrid& g = *grids[0];
     if (n == 0) return cudaSuccess;
-    if (g.method == 1 || g.ndims > 6 || g.nvals >= (size_t(1) << 31) || nf > kMaxFields) return cudaErrorNotSupported;
+    if (g.method == 1 || g.ndims > 6 || index64(g) || nf > kMaxFields) return cudaErrorNotSupported;
     FieldArgs<T> f{};
     f.nf = nf;
     const int patch = g.ndims >= 2 ? 4 : 2;

@@ -17,8 +17,11 @@ cudaError_t launch_linear_direct(const DeviceGrid& g, const T* const* obs, size_
         o.window = WL != 0;
         return o;
     };
-    if (g.nvals >= (size_t(1) << 31))  // 64-bit index arithmetic: the basic kernel only
-        return launch_generic<T, N>(linear_kernel<T, N, RECT, 0, 1, long long>, g, obs, n, out, first_bad, index_base, stream, opts(1));
+    if (index64(g)) {  // 64-bit index arithmetic: the basic kernel only, straight from `vals`
+        LaunchOpts o = opts(1);
+        o.window = false;
+        return launch_generic<T, N>(linear_kernel<T, N, RECT, 0, 1, long long>, g, obs, n, out, first_bad, index_base, stream, o);
+    }
     if (P > 1 && n >= static_cast<size_t>(P) && vector_aligned<T>(obs, N, out, P))
         return launch_generic<T, N>(linear_kernel<T, N, RECT, WL, P, int>, g, obs, n, out, first_bad, index_base, stream, opts(P));
     return launch_generic<T, N>(linear_kernel<T, N, RECT, WL, 1, int>, g, obs, n, out, first_bad, index_base, stream, opts(1));
@@ -62,7 +65,7 @@ cudaError_t launch_linear_n(const DeviceGrid& g, const T* const* obs, size_t n, 
         const size_t min_points = sweep_env("INTERPN_B200_SLAB_MIN_POINTS", 1 << 20);
         const size_t ctas = sweep_env("INTERPN_B200_SLAB_CTAS", 8);
         const size_t bytes = g.nvals * sizeof(T);
-        if (pass_kb && bytes > (min_kb << 10) && g.nvals < (size_t(1) << 31) && n >= min_points) {
+        if (pass_kb && bytes > (min_kb << 10) && !index64(g) && n >= min_points) {
             const int passes = static_cast<int>((bytes + (pass_kb << 10) - 1) / (pass_kb << 10));
             const int cells = g.dim[0] - 1;
             if (passes >= 2 && passes <= 8 && cells >= passes) {

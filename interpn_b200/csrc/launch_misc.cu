@@ -12,6 +12,11 @@ size_t sweep_env(const char* name, size_t fallback) {
 
 size_t sweep_env_common(const char* name, size_t fallback) { return sweep_env(name, fallback); }
 
+bool force_index64() {
+    const char* e = getenv("INTERPN_B200_INDEX64");
+    return e && e[0] == '1';
+}
+
 // ---------------------------------------------------------------------------------------------
 // Window layout builder: win[f*W + j] = vals[min(f + j, nvals - 1)]  (kernels.cuh load_row)
 // ---------------------------------------------------------------------------------------------
@@ -183,8 +188,9 @@ cudaError_t launch_one_dim(int kind, bool rect, T start, T step, const T* grid, 
     a.n = n;
     a.first_bad = first_bad;
     a.index_base = index_base;
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     unsigned grid_dim = grid_for(n, sms, 8);
     if (rect) one_dim_kernel<T, true><<<grid_dim, kBlock, 0, stream>>>(a);
     else one_dim_kernel<T, false><<<grid_dim, kBlock, 0, stream>>>(a);
@@ -221,8 +227,9 @@ __global__ void __launch_bounds__(kBlock) check_bounds_kernel(const T* __restric
 template <class T>
 cudaError_t launch_check_bounds(const T* x, size_t n, T lo, T hi, T atol, int* flag, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     check_bounds_kernel<T><<<grid_for(n, sms, 8), kBlock, 0, stream>>>(x, n, lo, hi, atol, flag);
     count_launch();
     return cudaGetLastError();

@@ -15,7 +15,7 @@ cudaError_t launch_nearest(const DeviceGrid& g, const T* const* obs, size_t n, T
     popts.points_per_thread = g.rect ? PR : P;
     const int pp = popts.points_per_thread;
     const bool vec = pp > 1 && n >= static_cast<size_t>(pp) && vector_aligned<T>(obs, g.ndims, out, pp);
-    if (g.nvals >= (size_t(1) << 31)) {  // 64-bit index arithmetic: the basic kernel only
+    if (index64(g)) {  // 64-bit index arithmetic: the basic kernel only
         if (g.rect) {
             IB200_SWITCH_N(6, err = (launch_generic<T, N>(nearest_kernel<T, N, true, 1, long long>, g, obs, n, out, first_bad, index_base, stream));)
         } else {

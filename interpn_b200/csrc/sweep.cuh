@@ -310,7 +310,7 @@ inline bool plan_sweep(const DeviceGrid& g, size_t n, int fp, int row_bytes_scal
     const size_t min_points = sweep_env("INTERPN_B200_SWEEP_MIN_POINTS", size_t(1) << 21);
     const size_t min_rows = sweep_env("INTERPN_B200_SWEEP_MIN_ROWS", 16);
     if (N < 2 || gathered <= min_bytes || n < min_points || static_cast<size_t>(rows) < min_rows) return false;
-    if (g.nvals >= (size_t(1) << 31) || (g.rect && !axes_in_smem)) return false;
+    if (index64(g) || (g.rect && !axes_in_smem)) return false;
     // Slab of the gathered array under one key. Multilinear evaluation is cheap next to the sort, and fewer, larger
     // slabs mean longer runs per (tile, key) in the scatter: 48 MB measured best on C4 (6.1 -> 7.2 G points/s; 96 MB
     // falls out of L2). The multicubic kernels dominate their sort and are flat between 6 and 24 MB.

@@ -244,3 +244,47 @@ def json_dtype(model) -> str:
     import json
 
     return json.loads(model.model_dump_json())["vals"]["dtype"]
+
+
+def test_models_stay_plain_data_after_evaluation(monkeypatch):
+    """the grid-resident device handle (a ctypes pointer) must not live in a model's state — the reference's
+    models are plain data and can be pickled, deep-copied and compared at any time."""
+    import copy
+    import ctypes
+    import gc
+    import pickle
+
+    import interpn_b200 as ib
+    from interpn_b200 import api
+
+    closed = []
+
+    class FakeResident:
+        def __init__(self):
+            self.handle = ctypes.c_void_p(0xDEAD)  # what makes a real Interpolator unpicklable
+
+        def eval(self, obs, out):
+            out[:] = 1.0
+            return out
+
+        def close(self):
+            closed.append(self)
+
+    for cls in (ib.MultilinearRegular, ib.MulticubicRegular, ib.NearestRegular):
+        monkeypatch.setattr(cls, "_build", lambda self: FakeResident())
+    m = ib.MulticubicRegular.new([4, 5], np.zeros(2), np.ones(2), np.arange(20.0))
+    fresh = ib.MulticubicRegular.new([4, 5], np.zeros(2), np.ones(2), np.arange(20.0))
+    assert m.eval([np.zeros(3), np.zeros(3)]).tolist() == [1.0, 1.0, 1.0]
+    assert id(m) in api._RESIDENT and id(fresh) not in api._RESIDENT
+    c = copy.deepcopy(m)
+    c2 = m.model_copy(deep=True)
+    p = pickle.loads(pickle.dumps(m))
+    for other in (c, c2, p):
+        assert id(other) not in api._RESIDENT  # a copy builds its own resident interpolator lazily
+        assert other.model_dump_json() == m.model_dump_json() == fresh.model_dump_json()
+        assert other.eval([np.zeros(2), np.zeros(2)]).tolist() == [1.0, 1.0]
+    assert m.__pydantic_private__ == fresh.__pydantic_private__  # nothing hidden distinguishes an evaluated model
+    key = id(m)
+    del m
+    gc.collect()
+    assert key not in api._RESIDENT and len(closed) == 1  # the handle is released with its model

@@ -88,6 +88,18 @@ const char* interpn_b200_last_error_detail(void);
 int interpn_b200_device_count(void);
 /* Select the CUDA device used by subsequent calls on this host thread (cudaSetDevice). */
 int interpn_b200_set_device(int device);
+/* How many GPUs ONE host-buffer call may use (the one-shot functions and interpn_b200_interp_eval_host_*): the query
+ * batch is cut into chunks that the devices pull from a shared counter, each evaluating on its own replica of the grid
+ * (copied device-to-device on first use) — BASELINE north_star: "multi-GPU runs shard the query batch ... with the
+ * grid replicated once". n = 0 (the default, or INTERPN_B200_HOST_DEVICES unset/0): every visible sm_100 device;
+ * n = 1: only the interpolator's own device (what a one-process-per-GPU launcher such as torchrun wants). Batches
+ * below 2^22 points always stay on one device. Results, the failure index and the "earlier outputs written, later
+ * untouched" rule are the same for any n. */
+int interpn_b200_set_host_devices(int n);
+int interpn_b200_host_devices(void);
+/* Host threads that copy PAGEABLE caller memory to and from pinned staging buffers (INTERPN_B200_COPY_THREADS; pinned
+ * caller memory is DMA'd in place). */
+int interpn_b200_copy_threads(void);
 /* Number of kernels this library has launched in this process (all threads); bench.py reports the delta. */
 uint64_t interpn_b200_launch_count(void);
 /* How many of those launches were bin-swept evaluations (grids beyond L2, interpn_b200/csrc/sweep.cuh). */
@@ -176,7 +188,8 @@ typedef struct interpn_b200_interp interpn_b200_interp;
                                               size_t ngrids, const T* vals, size_t nvals,                         \
                                               int linearize_extrapolation, int vals_location,                     \
                                               interpn_b200_interp** out_interp);                                  \
-    /* `.interp(obs, out)` on HOST buffers (copies in/out, synchronous, reference error semantics). */            \
+    /* `.interp(obs, out)` on HOST buffers (copies in/out, synchronous, reference error semantics); pageable or   \
+     * pinned memory, one or several GPUs (interpn_b200_set_host_devices). */                                     \
     int interpn_b200_interp_eval_host_##SUFFIX(interpn_b200_interp* interp, const T* const* obs,                  \
                                                const size_t* obs_lens, size_t nobs, T* out, size_t nout,          \
                                                size_t* first_bad);                                                \

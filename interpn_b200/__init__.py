@@ -16,7 +16,16 @@ There is no CPU fallback: importing fails without the built library and compute 
 from __future__ import annotations
 
 from . import _lib, one_dim, raw
-from ._lib import InterpnDeviceError, device_count, launch_count, set_device, swept_launch_count
+from ._lib import (
+    InterpnDeviceError,
+    copy_threads,
+    device_count,
+    host_devices,
+    launch_count,
+    set_device,
+    set_host_devices,
+    swept_launch_count,
+)
 from .interpolator import Interpolator
 from .api import (
     MulticubicRectilinear,
@@ -43,8 +52,11 @@ __all__ = [
     "MulticubicRectilinear",
     "NearestRegular",
     "NearestRectilinear",
+    "copy_threads",
     "device_count",
+    "host_devices",
     "launch_count",
     "set_device",
+    "set_host_devices",
     "swept_launch_count",
 ]

@@ -99,3 +99,18 @@ def device_count() -> int:
 
 def set_device(device: int) -> None:
     check(lib.interpn_b200_set_device(C.c_int(device)))
+
+
+def set_host_devices(n: int) -> None:
+    """How many GPUs one host-buffer call (``raw.*``, ``Interpolator.eval``, the model classes) may use: 0 = every
+    visible device (the default), 1 = only the interpolator's own (one process per GPU, e.g. under torchrun)."""
+    check(lib.interpn_b200_set_host_devices(C.c_int(n)))
+
+
+def host_devices() -> int:
+    return int(lib.interpn_b200_host_devices())
+
+
+def copy_threads() -> int:
+    """Host threads that stage pageable caller memory (INTERPN_B200_COPY_THREADS)."""
+    return int(lib.interpn_b200_copy_threads())

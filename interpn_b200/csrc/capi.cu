@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -60,138 +61,9 @@ static int require_device(int* sm_count = nullptr) {
     return INTERPN_B200_OK;
 }
 
-// ---------------------------------------------------------------------------------------------
-// Host<->device pipeline for host-buffer calls: NSLOT chunks in flight, each on its own stream,
-// so the H2D copy of chunk k+1 overlaps the kernel of chunk k and the D2H copy of chunk k-1.
-// Output chunks are released to the caller's buffer only after that chunk's failure flag has
-// been read, which reproduces the reference's "stop at the first failing point" semantics.
-// ---------------------------------------------------------------------------------------------
-
-constexpr int kSlots = 3;
-constexpr size_t kChunkBytesPerArray = size_t(32) << 20;  // 32 MiB per coordinate array per chunk
-
-struct Slot {
-    void* in[kMaxNd] = {};
-    void* out = nullptr;
-    unsigned long long* flag_dev = nullptr;
-    unsigned long long* flag_host = nullptr;  // pinned
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ready = nullptr;
-};
-
-struct HostPipeline {
-    Slot slot[kSlots];
-    size_t cap_bytes = 0;  // per array
-    int cap_nin = 0;
-    bool has_streams = false;
-
-    int ensure(int nin, size_t bytes_per_array) {
-        if (!has_streams) {
-            for (auto& s : slot) {
-                CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-                CUDA_TRY(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
-                CUDA_TRY(cudaMalloc(&s.flag_dev, sizeof(unsigned long long)));
-                CUDA_TRY(cudaMallocHost(&s.flag_host, sizeof(unsigned long long)));
-            }
-            has_streams = true;
-        }
-        if (bytes_per_array > cap_bytes || nin > cap_nin) {
-            release_buffers();
-            size_t b = bytes_per_array > cap_bytes ? bytes_per_array : cap_bytes;
-            int k = nin > cap_nin ? nin : cap_nin;
-            for (auto& s : slot) {
-                for (int j = 0; j < k; ++j) CUDA_TRY(cudaMalloc(&s.in[j], b));
-                CUDA_TRY(cudaMalloc(&s.out, b));
-            }
-            cap_bytes = b;
-            cap_nin = k;
-        }
-        return INTERPN_B200_OK;
-    }
-
-    void release_buffers() {
-        for (auto& s : slot) {
-            for (auto& p : s.in) {
-                if (p) cudaFree(p);
-                p = nullptr;
-            }
-            if (s.out) cudaFree(s.out);
-            s.out = nullptr;
-        }
-        cap_bytes = 0;
-        cap_nin = 0;
-    }
-
-    ~HostPipeline() {
-        release_buffers();
-        if (has_streams) {
-            for (auto& s : slot) {
-                cudaStreamDestroy(s.stream);
-                cudaEventDestroy(s.ready);
-                cudaFree(s.flag_dev);
-                cudaFreeHost(s.flag_host);
-            }
-        }
-    }
-
-    // launch(in_dev[], out_dev, count, flag_dev, index_base, stream) -> cudaError_t
-    // out_host may be NULL (reduction-style kernels with no per-point output).
-    template <class F>
-    int run(const void* const* in_host, int nin, void* out_host, size_t n, size_t elem, F&& launch,
-            size_t* first_bad) {
-        if (first_bad) *first_bad = SIZE_MAX;
-        if (n == 0) return INTERPN_B200_OK;
-        const size_t chunk = n < kChunkBytesPerArray / elem ? n : kChunkBytesPerArray / elem;
-        int st = ensure(nin, chunk * elem);
-        if (st != INTERPN_B200_OK) return st;
-        const size_t nchunks = (n + chunk - 1) / chunk;
-        size_t bad = SIZE_MAX;
-
-        // Retire chunk c: wait for its kernel + flag, then release its output to the caller.
-        auto retire = [&](size_t c) -> int {
-            Slot& s = slot[c % kSlots];
-            CUDA_TRY(cudaEventSynchronize(s.ready));
-            const size_t lo = c * chunk;
-            size_t cnt = (n - lo) < chunk ? (n - lo) : chunk;
-            const unsigned long long flag = *s.flag_host;
-            if (flag != ~0ull) {
-                bad = static_cast<size_t>(flag);
-                cnt = bad - lo;  // only the prefix before the failing point is written back
-            }
-            if (out_host && cnt)
-                CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(out_host) + lo * elem, s.out, cnt * elem,
-                                         cudaMemcpyDeviceToHost, s.stream));
-            return INTERPN_B200_OK;
-        };
-
-        for (size_t c = 0; c < nchunks && bad == SIZE_MAX; ++c) {
-            Slot& s = slot[c % kSlots];
-            const size_t lo = c * chunk;
-            const size_t cnt = (n - lo) < chunk ? (n - lo) : chunk;
-            for (int j = 0; j < nin; ++j)
-                CUDA_TRY(cudaMemcpyAsync(s.in[j], static_cast<const char*>(in_host[j]) + lo * elem, cnt * elem,
-                                         cudaMemcpyHostToDevice, s.stream));
-            CUDA_TRY(cudaMemsetAsync(s.flag_dev, 0xff, sizeof(unsigned long long), s.stream));
-            CUDA_TRY(launch(s.in, s.out, cnt, s.flag_dev, static_cast<unsigned long long>(lo), s.stream));
-            CUDA_TRY(cudaMemcpyAsync(s.flag_host, s.flag_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
-                                     s.stream));
-            CUDA_TRY(cudaEventRecord(s.ready, s.stream));
-            if (c >= 1) {
-                st = retire(c - 1);
-                if (st != INTERPN_B200_OK) return st;
-            }
-        }
-        if (bad == SIZE_MAX) {
-            st = retire(nchunks - 1);
-            if (st != INTERPN_B200_OK) return st;
-        }
-        for (auto& s : slot) CUDA_TRY(cudaStreamSynchronize(s.stream));
-        if (first_bad) *first_bad = bad;
-        return bad == SIZE_MAX ? INTERPN_B200_OK : INTERPN_B200_ERR_UNREPRESENTABLE;
-    }
-};
-
 }  // namespace ib200
+
+#include "host_exec.cuh"
 
 using namespace ib200;
 
@@ -200,7 +72,15 @@ struct interpn_b200_interp {
     DeviceGrid g;
     int device = 0;
     unsigned long long* first_bad_dev = nullptr;  // latched by eval_device launches
-    HostPipeline pipe;                            // lazily sized by eval_host
+    // Host-buffer evaluation (host_exec.cuh): slots of the home device, and — when one call may use several GPUs — one
+    // replica of the grid per further device, copied device-to-device on first use and dropped by vals_updated().
+    DeviceSlots home;
+    struct Replica {
+        DeviceGrid g;
+        DeviceSlots slots;
+    };
+    std::vector<Replica*> replicas;
+    std::mutex host_mu;  // one host-buffer evaluation per interpolator at a time
 };
 
 namespace {
@@ -588,6 +468,91 @@ int rect_new(int method, const T* const* grids, const size_t* grid_lens, size_t 
     return INTERPN_B200_OK;
 }
 
+// ---- several devices behind one host-buffer call (host_exec.cuh) -----------------------------------
+
+constexpr size_t kMultiDeviceMinPoints = size_t(1) << 22;  // below this one GPU finishes before a second one has its grid
+std::atomic<int> g_host_devices{-1};                       // -1: INTERPN_B200_HOST_DEVICES or every visible device
+
+int host_device_limit() {
+    int want = g_host_devices.load(std::memory_order_relaxed);
+    if (want < 0) {
+        const char* e = getenv("INTERPN_B200_HOST_DEVICES");
+        want = e && *e ? atoi(e) : 0;
+    }
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) {
+        cudaGetLastError();
+        return 1;
+    }
+    return want <= 0 || want > count ? count : want;
+}
+
+void free_replicas(interpn_b200_interp* h) {
+    int home = 0;
+    cudaGetDevice(&home);
+    for (auto* r : h->replicas) {
+        cudaSetDevice(r->slots.device);
+        r->slots.destroy();
+        if (r->g.vals) cudaFree(r->g.vals);
+        if (r->g.win) cudaFree(r->g.win);
+        if (r->g.axes) cudaFree(r->g.axes);
+        delete r;
+    }
+    h->replicas.clear();
+    cudaSetDevice(home);
+}
+
+// Replicates the resident grid (vals, its window copy, the axes blob) onto the next `want - 1` sm_100 devices after the
+// interpolator's own: device-to-device copies (NVLink peer copies where the devices are peers), once per interpolator.
+int ensure_replicas(interpn_b200_interp* h, int want) {
+    int count = 0;
+    CUDA_TRY(cudaGetDeviceCount(&count));
+    const DeviceGrid& g = h->g;
+    const size_t bytes = g.nvals * static_cast<size_t>(g.elem);
+    for (int k = 1; k < count && static_cast<int>(h->replicas.size()) + 1 < want; ++k) {
+        const int dev = (h->device + k) % count;
+        bool have = false;
+        for (auto* r : h->replicas) have = have || r->slots.device == dev;
+        if (have) continue;
+        int major = 0, sms = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+        if (major != 10) continue;
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        auto* r = new (std::nothrow) interpn_b200_interp::Replica();
+        if (!r) return INTERPN_B200_ERR_TOO_LARGE;
+        r->g = g;
+        r->g.vals = r->g.win = r->g.axes = nullptr;
+        r->g.sm_count = sms;
+        r->slots.device = dev;
+        h->replicas.push_back(r);  // owned from here on (freed with the interpolator even if a copy below fails)
+        CUDA_TRY(cudaSetDevice(dev));
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, dev, h->device) == cudaSuccess && can) {
+            cudaDeviceEnablePeerAccess(h->device, 0);  // already-enabled is fine
+            cudaGetLastError();
+        }
+        CUDA_TRY(cudaMalloc(&r->g.vals, bytes ? bytes : 1));
+        CUDA_TRY(cudaMemcpyPeer(r->g.vals, dev, g.vals, h->device, bytes));
+        if (g.win) {
+            CUDA_TRY(cudaMalloc(&r->g.win, bytes * g.win_width));
+            CUDA_TRY(cudaMemcpyPeer(r->g.win, dev, g.win, h->device, bytes * g.win_width));
+        }
+        if (g.axes) {
+            CUDA_TRY(cudaMalloc(&r->g.axes, static_cast<size_t>(g.axes_total) * g.elem));
+            CUDA_TRY(cudaMemcpyPeer(r->g.axes, dev, g.axes, h->device, static_cast<size_t>(g.axes_total) * g.elem));
+        }
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+        CUDA_TRY(cudaDeviceSynchronize());
+    }
+    CUDA_TRY(cudaSetDevice(h->device));
+    return INTERPN_B200_OK;
+}
+
 template <class T>
 int eval_host(interpn_b200_interp* h, const T* const* obs, const size_t* obs_lens, size_t nobs, T* out, size_t nout,
               size_t* first_bad) {
@@ -598,19 +563,42 @@ int eval_host(interpn_b200_interp* h, const T* const* obs, const size_t* obs_len
     if (st != INTERPN_B200_OK) return st;
     if (nout == 0) return INTERPN_B200_OK;
     if (!out) return INTERPN_B200_ERR_INVALID_ARG;
-    CUDA_TRY(cudaSetDevice(h->device));
     const void* in_host[kMaxNd];
     for (size_t j = 0; j < nobs; ++j) in_host[j] = obs[j];
-    const DeviceGrid& g = h->g;
-    return h->pipe.run(
-        in_host, static_cast<int>(nobs), out, nout, sizeof(T),
-        [&](void* const* in_dev, void* out_dev, size_t cnt, unsigned long long* flag, unsigned long long base,
+    std::lock_guard<std::mutex> lk(h->host_mu);
+    int home = 0;
+    CUDA_TRY(cudaGetDevice(&home));
+    CUDA_TRY(cudaSetDevice(h->device));
+    // Devices of this call: the interpolator's own, plus replicas on the other devices the process may use
+    // (interpn_b200_set_host_devices) when the batch is large enough to feed them.
+    DeviceSlots* devs[64];
+    const DeviceGrid* grids[64];
+    int ndev = 1;
+    devs[0] = &h->home;
+    grids[0] = &h->g;
+    h->home.device = h->device;
+    const int want = host_device_limit();
+    if (want > 1 && nout >= kMultiDeviceMinPoints) {
+        int st2 = ensure_replicas(h, want);
+        if (st2 != INTERPN_B200_OK) return st2;
+        for (auto* r : h->replicas) {
+            if (ndev >= want || ndev >= 64) break;
+            devs[ndev] = &r->slots;
+            grids[ndev] = &r->g;
+            ++ndev;
+        }
+    }
+    st = run_host_batch(
+        devs, ndev, in_host, static_cast<int>(nobs), out, nout, sizeof(T),
+        [&](int di, void* const* in_dev, void* out_dev, size_t cnt, unsigned long long* flag, unsigned long long base,
             cudaStream_t s) {
             const T* o[kMaxNd];
             for (size_t j = 0; j < nobs; ++j) o[j] = static_cast<const T*>(in_dev[j]);
-            return launch_eval<T>(g, o, cnt, static_cast<T*>(out_dev), flag, base, s);
+            return launch_eval<T>(*grids[di], o, cnt, static_cast<T*>(out_dev), flag, base, s);
         },
         first_bad);
+    cudaSetDevice(home);
+    return st;
 }
 
 template <class T>
@@ -730,9 +718,10 @@ int check_bounds_axes(const T* lo, const T* hi, size_t ndims, const T* const* ob
             const void* in_host[1] = {obs[d]};
             int* flag = flags_dev + d;
             const T l = lo[d], h = hi[d];
-            int s = pipe.run(
-                in_host, 1, nullptr, obs_lens[d], sizeof(T),
-                [&](void* const* in_dev, void*, size_t cnt, unsigned long long*, unsigned long long, cudaStream_t stream) {
+            DeviceSlots* devs[1] = {&pipe.dev};
+            int s = run_host_batch(
+                devs, 1, in_host, 1, nullptr, obs_lens[d], sizeof(T),
+                [&](int, void* const* in_dev, void*, size_t cnt, unsigned long long*, unsigned long long, cudaStream_t stream) {
                     return launch_check_bounds<T>(static_cast<const T*>(in_dev[0]), cnt, l, h, atol, flag, stream);
                 },
                 nullptr);
@@ -824,9 +813,10 @@ int one_dim_host(int kind, bool rect, T start, T step, const T* grid, size_t ngr
             CUDA_TRY(cudaMemcpy(grid_dev, grid, ngrid * sizeof(T), cudaMemcpyHostToDevice));
         }
         const void* in_host[1] = {locs};
-        int s = pipe.run(
-            in_host, 1, out, nlocs, sizeof(T),
-            [&](void* const* in_dev, void* out_dev, size_t cnt, unsigned long long* flag, unsigned long long base,
+        DeviceSlots* devs[1] = {&pipe.dev};
+        int s = run_host_batch(
+            devs, 1, in_host, 1, out, nlocs, sizeof(T),
+            [&](int, void* const* in_dev, void* out_dev, size_t cnt, unsigned long long* flag, unsigned long long base,
                 cudaStream_t stream) {
                 return launch_one_dim<T>(kind, rect, start, step, grid_dev, vals_dev, nvals,
                                          static_cast<const T*>(in_dev[0]), cnt, static_cast<T*>(out_dev), flag, base,
@@ -887,6 +877,14 @@ int interpn_b200_set_device(int device) {
     CUDA_TRY(cudaSetDevice(device));
     return INTERPN_B200_OK;
 }
+
+int interpn_b200_set_host_devices(int n) {
+    if (n < 0) return INTERPN_B200_ERR_INVALID_ARG;
+    g_host_devices.store(n, std::memory_order_relaxed);
+    return INTERPN_B200_OK;
+}
+int interpn_b200_host_devices(void) { return host_device_limit(); }
+int interpn_b200_copy_threads(void) { return CopyPool::get().threads() + 1; }
 
 int interpn_b200_arithmetic(void) { return IB200_ARITH_FMA; }
 uint64_t interpn_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
@@ -1009,6 +1007,8 @@ void* interpn_b200_interp_vals_ptr(interpn_b200_interp* interp) { return interp 
 int interpn_b200_interp_vals_updated(interpn_b200_interp* interp, void* stream) {
     if (!interp) return INTERPN_B200_ERR_INVALID_ARG;
     CUDA_TRY(launch_build_window(interp->g, static_cast<cudaStream_t>(stream)));
+    std::lock_guard<std::mutex> lk(interp->host_mu);
+    free_replicas(interp);  // stale copies of the old values: rebuilt on the next multi-device call
     return INTERPN_B200_OK;
 }
 size_t interpn_b200_interp_vals_len(const interpn_b200_interp* interp) { return interp ? interp->g.nvals : 0; }
@@ -1017,10 +1017,16 @@ size_t interpn_b200_interp_ndims(const interpn_b200_interp* interp) { return int
 
 void interpn_b200_interp_free(interpn_b200_interp* interp) {
     if (!interp) return;
+    free_replicas(interp);
+    int home = 0;
+    cudaGetDevice(&home);
+    cudaSetDevice(interp->device);
+    interp->home.destroy();
     if (interp->g.vals) cudaFree(interp->g.vals);
     if (interp->g.win) cudaFree(interp->g.win);
     if (interp->g.axes) cudaFree(interp->g.axes);
     if (interp->first_bad_dev) cudaFree(interp->first_bad_dev);
+    cudaSetDevice(home);
     delete interp;
 }
 

@@ -116,7 +116,10 @@ class Interpolator:
         out = _arr(out, self.dtype, "out", writable=True)
         optrs, olens = _ptrs(obs, self._ct)
         fn = getattr(lib, f"interpn_b200_interp_eval_host_{self._sfx}")
-        _lib.check(fn(self._h, optrs, olens, C.c_size_t(len(obs)), _p(out, self._ct), C.c_size_t(out.size), None))
+        fb = C.c_size_t(_lib.NO_BAD)
+        st = fn(self._h, optrs, olens, C.c_size_t(len(obs)), _p(out, self._ct), C.c_size_t(out.size), C.byref(fb))
+        self.first_bad = None if fb.value == _lib.NO_BAD else int(fb.value)
+        _lib.check(st)
         return out
 
     def eval_device(self, obs_ptrs: Sequence[int], n: int, out_ptr: int, stream: int = 0) -> None:

@@ -318,11 +318,21 @@ inline T cubic_rect_inner(const T* v, const T* g, T x, Saturation sat, bool line
 // Both visit the same arithmetic DAG; they are kept separate so the tests can assert that.
 // ---------------------------------------------------------------------------------------------
 
-template <int FP, class T, class Reduce>
-inline T tree_flattened(int n, const size_t* origin, const size_t* dimprod, const T* vals, Reduce reduce) {
+// NC > 0: the dimensionality is a compile-time constant (the reference's structs are const-generic and unroll these loops
+// with crunchy::unroll!, multilinear/regular.rs:347-403), so the timed CPU baseline is not slowed by index arithmetic
+// the crate never executes. Same operations on the same values in the same order as NC = 0; tests compare the two.
+constexpr size_t ipow(size_t b, int e) { return e == 0 ? 1 : b * ipow(b, e - 1); }
+
+template <int FP, int NC = 0, class T, class Reduce>
+inline __attribute__((always_inline)) T tree_flattened(int n_rt, const size_t* origin, const size_t* dimprod, const T* vals, Reduce reduce) {
+    const int n = NC ? NC : n_rt;
     T store[MAXDIMS][FP];
     size_t nverts = 1;
     for (int i = 0; i < n; ++i) nverts *= FP;
+    if (NC) nverts = ipow(FP, NC);
+    // fully unrolled up to 64 vertices; a 4-D cubic footprint (256) is unrolled by 64 — the dimension-3 bookkeeping stays
+    // in the loop, everything below it is constant (keeps the build of this checker to a minute)
+#pragma GCC unroll 64
     for (size_t i = 0; i < nverts; ++i) {
         size_t idx = 0, rem = i;
         for (int k = 0; k < n; ++k) {
@@ -360,14 +370,14 @@ inline T tree_recursive(int dim, const size_t* origin, size_t* loc, const size_t
     return reduce(v, next);
 }
 
-template <int FP, bool RECURSIVE, class T, class Reduce>
-inline T tree(int n, const size_t* origin, const size_t* dimprod, const T* vals, Reduce reduce) {
+template <int FP, bool RECURSIVE, int NC = 0, class T, class Reduce>
+inline __attribute__((always_inline)) T tree(int n, const size_t* origin, const size_t* dimprod, const T* vals, Reduce reduce) {
     if (RECURSIVE) {
         size_t loc[MAXDIMS];
         for (int i = 0; i < n; ++i) loc[i] = origin[i];
         return tree_recursive<FP>(n, origin, loc, dimprod, n, vals, reduce);
     }
-    return tree_flattened<FP>(n, origin, dimprod, vals, reduce);
+    return tree_flattened<FP, NC>(n, origin, dimprod, vals, reduce);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -376,9 +386,10 @@ inline T tree(int n, const size_t* origin, const size_t* dimprod, const T* vals,
 
 // ref: multilinear/regular.rs:296-404; recursive twin regular_recursive.rs:274-323
 // (the twin never fuses index_zero_loc, regular_recursive.rs:310-313).
-template <bool FMA, bool RECURSIVE, class T>
-inline bool linear_regular_one(int n, const size_t* dims, const T* starts, const T* steps, const T* vals, const T* x,
+template <bool FMA, bool RECURSIVE, int NC = 0, class T>
+inline bool linear_regular_one(int n_rt, const size_t* dims, const T* starts, const T* steps, const T* vals, const T* x,
                                T& out) {
+    const int n = NC ? NC : n_rt;
     size_t origin[MAXDIMS], dimprod[MAXDIMS];
     T dts[MAXDIMS];
     c_strides(n, dims, dimprod);
@@ -388,7 +399,7 @@ inline bool linear_regular_one(int n, const size_t* dims, const T* starts, const
         T zero_loc = muladd<(FMA && !RECURSIVE)>(steps[i], origin_f, starts[i]);
         dts[i] = (x[i] - zero_loc) / steps[i];
     }
-    out = tree<2, RECURSIVE>(n, origin, dimprod, vals, [&](const T* s, int d) {
+    out = tree<2, RECURSIVE, NC>(n, origin, dimprod, vals, [&](const T* s, int d) {
         T y0 = s[0];
         T dy = s[1] - y0;
         return muladd<FMA>(dts[d], dy, y0);
@@ -397,12 +408,13 @@ inline bool linear_regular_one(int n, const size_t* dims, const T* starts, const
 }
 
 // ref: multilinear/rectilinear.rs:244-346; recursive twin rectilinear_recursive.rs:224-336
-template <bool FMA, bool RECURSIVE, class T>
-inline void linear_rect_one(int n, const size_t* dims, const T* const* grids, const T* vals, const T* x, T& out) {
+template <bool FMA, bool RECURSIVE, int NC = 0, class T>
+inline void linear_rect_one(int n_rt, const size_t* dims, const T* const* grids, const T* vals, const T* x, T& out) {
+    const int n = NC ? NC : n_rt;
     size_t origin[MAXDIMS], dimprod[MAXDIMS];
     c_strides(n, dims, dimprod);
     for (int i = 0; i < n; ++i) origin[i] = rect_loc2(x[i], grids[i], dims[i]);
-    out = tree<2, RECURSIVE>(n, origin, dimprod, vals, [&](const T* s, int d) {
+    out = tree<2, RECURSIVE, NC>(n, origin, dimprod, vals, [&](const T* s, int d) {
         T x0 = grids[d][origin[d]];
         T x1 = grids[d][origin[d] + 1];
         T step = x1 - x0;
@@ -414,9 +426,10 @@ inline void linear_rect_one(int n, const size_t* dims, const T* const* grids, co
 }
 
 // ref: multicubic/regular.rs:325-422; recursive twin regular_recursive.rs:322-376
-template <bool FMA, bool RECURSIVE, class T>
-inline bool cubic_regular_one(int n, const size_t* dims, const T* starts, const T* steps, const T* vals,
+template <bool FMA, bool RECURSIVE, int NC = 0, class T>
+inline bool cubic_regular_one(int n_rt, const size_t* dims, const T* starts, const T* steps, const T* vals,
                               bool linearize, const T* x, T& out) {
+    const int n = NC ? NC : n_rt;
     size_t origin[MAXDIMS], dimprod[MAXDIMS];
     Saturation sat[MAXDIMS];
     T dts[MAXDIMS];
@@ -426,21 +439,22 @@ inline bool cubic_regular_one(int n, const size_t* dims, const T* starts, const 
         T one_loc = starts[i] + steps[i] * static_cast<T>(origin[i] + 1);  // never fused (regular.rs:356-359)
         dts[i] = (x[i] - one_loc) / steps[i];
     }
-    out = tree<4, RECURSIVE>(n, origin, dimprod, vals, [&](const T* s, int d) {
+    out = tree<4, RECURSIVE, NC>(n, origin, dimprod, vals, [&](const T* s, int d) {
         return cubic_regular_inner<FMA, RECURSIVE>(s, dts[d], sat[d], linearize);
     });
     return true;
 }
 
 // ref: multicubic/rectilinear.rs:265-356; recursive twin rectilinear_recursive.rs:242-284
-template <bool FMA, bool RECURSIVE, class T>
-inline void cubic_rect_one(int n, const size_t* dims, const T* const* grids, const T* vals, bool linearize,
+template <bool FMA, bool RECURSIVE, int NC = 0, class T>
+inline void cubic_rect_one(int n_rt, const size_t* dims, const T* const* grids, const T* vals, bool linearize,
                            const T* x, T& out) {
+    const int n = NC ? NC : n_rt;
     size_t origin[MAXDIMS], dimprod[MAXDIMS];
     Saturation sat[MAXDIMS];
     c_strides(n, dims, dimprod);
     for (int i = 0; i < n; ++i) cubic_rect_loc(x[i], grids[i], dims[i], origin[i], sat[i]);
-    out = tree<4, RECURSIVE>(n, origin, dimprod, vals, [&](const T* s, int d) {
+    out = tree<4, RECURSIVE, NC>(n, origin, dimprod, vals, [&](const T* s, int d) {
         return cubic_rect_inner<FMA, RECURSIVE>(s, grids[d] + origin[d], x[d], sat[d], linearize);
     });
 }

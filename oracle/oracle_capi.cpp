@@ -111,6 +111,34 @@ int regular_impl(int method, const size_t* dims, size_t ndims, const T* starts, 
     };
 #define ORACLE_RUN(EXPR) \
     return run_batch(nout, nthreads, first_bad, [&](size_t i) { T x[MAXDIMS]; gather(i, x); return (EXPR); })
+// The reference's dispatch order with the dimensionality as a compile-time constant, like its const-generic structs
+// (order == 0 only; the forced orders keep the runtime-N twins so the tests can compare the two).
+#define ORACLE_RUN_N(NC, FN, ...)                                                                       \
+    return run_batch(nout, nthreads, first_bad, [&](size_t i) {                                         \
+        T x[MAXDIMS];                                                                                   \
+        for (int j = 0; j < NC; ++j) x[j] = obs[j][i];                                                  \
+        return fma ? FN<true, false, NC>(__VA_ARGS__) : FN<false, false, NC>(__VA_ARGS__);              \
+    })
+    if (order == 0 && method == 0) {
+        switch (n) {
+            case 1: ORACLE_RUN_N(1, linear_regular_one, n, dims, starts, steps, vals, x, out[i]);
+            case 2: ORACLE_RUN_N(2, linear_regular_one, n, dims, starts, steps, vals, x, out[i]);
+            case 3: ORACLE_RUN_N(3, linear_regular_one, n, dims, starts, steps, vals, x, out[i]);
+            case 4: ORACLE_RUN_N(4, linear_regular_one, n, dims, starts, steps, vals, x, out[i]);
+            case 5: ORACLE_RUN_N(5, linear_regular_one, n, dims, starts, steps, vals, x, out[i]);
+            case 6: ORACLE_RUN_N(6, linear_regular_one, n, dims, starts, steps, vals, x, out[i]);
+            default: break;
+        }
+    }
+    if (order == 0 && cubic) {
+        switch (n) {
+            case 1: ORACLE_RUN_N(1, cubic_regular_one, n, dims, starts, steps, vals, lin, x, out[i]);
+            case 2: ORACLE_RUN_N(2, cubic_regular_one, n, dims, starts, steps, vals, lin, x, out[i]);
+            case 3: ORACLE_RUN_N(3, cubic_regular_one, n, dims, starts, steps, vals, lin, x, out[i]);
+            case 4: ORACLE_RUN_N(4, cubic_regular_one, n, dims, starts, steps, vals, lin, x, out[i]);
+            default: break;
+        }
+    }
     if (method == 0) {
         const bool rec = use_recursive(order, ndims, 6);
         if (fma && rec) ORACLE_RUN((linear_regular_one<true, true>(n, dims, starts, steps, vals, x, out[i])));
@@ -154,6 +182,34 @@ int rectilinear_impl(int method, const T* const* grids, const size_t* grid_lens,
     auto gather = [&](size_t i, T* x) {
         for (int j = 0; j < n; ++j) x[j] = obs[j][i];
     };
+#define ORACLE_RECT_N(NC, FN, ...)                                                                      \
+    return run_batch(nout, nthreads, first_bad, [&](size_t i) {                                         \
+        T x[MAXDIMS];                                                                                   \
+        for (int j = 0; j < NC; ++j) x[j] = obs[j][i];                                                  \
+        if (fma) FN<true, false, NC>(__VA_ARGS__);                                                      \
+        else FN<false, false, NC>(__VA_ARGS__);                                                         \
+        return true;                                                                                    \
+    })
+    if (order == 0 && method == 0) {
+        switch (n) {
+            case 1: ORACLE_RECT_N(1, linear_rect_one, n, dims, grids, vals, x, out[i]);
+            case 2: ORACLE_RECT_N(2, linear_rect_one, n, dims, grids, vals, x, out[i]);
+            case 3: ORACLE_RECT_N(3, linear_rect_one, n, dims, grids, vals, x, out[i]);
+            case 4: ORACLE_RECT_N(4, linear_rect_one, n, dims, grids, vals, x, out[i]);
+            case 5: ORACLE_RECT_N(5, linear_rect_one, n, dims, grids, vals, x, out[i]);
+            case 6: ORACLE_RECT_N(6, linear_rect_one, n, dims, grids, vals, x, out[i]);
+            default: break;
+        }
+    }
+    if (order == 0 && cubic) {
+        switch (n) {
+            case 1: ORACLE_RECT_N(1, cubic_rect_one, n, dims, grids, vals, lin, x, out[i]);
+            case 2: ORACLE_RECT_N(2, cubic_rect_one, n, dims, grids, vals, lin, x, out[i]);
+            case 3: ORACLE_RECT_N(3, cubic_rect_one, n, dims, grids, vals, lin, x, out[i]);
+            case 4: ORACLE_RECT_N(4, cubic_rect_one, n, dims, grids, vals, lin, x, out[i]);
+            default: break;
+        }
+    }
     if (method == 0) {
         const bool rec = use_recursive(order, ndims, 6);
         if (fma && rec) ORACLE_RUN((linear_rect_one<true, true>(n, dims, grids, vals, x, out[i]), true));

@@ -162,6 +162,26 @@ def test_flattened_and_recursive_orders_agree_bitwise(oracle, method, maxn, dtyp
             assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
 
 
+@pytest.mark.parametrize("fma", [False, True])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("method,maxn", [("linear", 6), ("cubic", 4)])
+def test_const_dimension_fast_path_equals_the_runtime_dimension_twin(oracle, method, maxn, dtype, fma):
+    """order="reference" runs the flattened range (linear N<=6, cubic N<=4) with the dimensionality as a compile-time
+    constant (the timed CPU baseline, like the crate's const-generic structs); order="flattened" keeps the runtime-N
+    loops. Same operations, same order: identical bits in both arithmetic modes."""
+    rng = np.random.default_rng(17)
+    lo = 4 if method == "cubic" else 2
+    for ndims in range(1, maxn + 1):
+        dims, grids, starts, steps, vals, obs = _random_case(rng, ndims, 500, lo, lo + 3, dtype)
+        for lin in (False, True):
+            a = oracle.interpn_regular(method, dims, starts, steps, vals, obs, linearize_extrapolation=lin, fma=fma, order="reference")
+            b = oracle.interpn_regular(method, dims, starts, steps, vals, obs, linearize_extrapolation=lin, fma=fma, order="flattened")
+            assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+            a = oracle.interpn_rectilinear(method, grids, vals, obs, linearize_extrapolation=lin, fma=fma, order="reference")
+            b = oracle.interpn_rectilinear(method, grids, vals, obs, linearize_extrapolation=lin, fma=fma, order="flattened")
+            assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
 def test_threads_match_serial(oracle):
     rng = np.random.default_rng(11)
     dims, grids, starts, steps, vals, obs = _random_case(rng, 3, 10007, 5, 9)

@@ -50,15 +50,15 @@ for step in "$@"; do
       ( time timeout 1800 python bench.py ${b//,/ } ) > $out/$name.json 2> $out/$name.err; echo "bench $name exit $?"
       summary $out/$name.json $name; tail -n 4 $out/$name.err ;;
     line)
-      timeout 900 python bench.py --workload $a --points $b --steps 5 --warmup 3 --no-cpu-baseline --no-e2e ${c//,/ } > $out/$a.json 2> $out/$a.err
+      timeout 900 python bench.py --workload $a --points $b --steps 5 --warmup 3 --no-cpu-baseline --no-e2e --sustained-steps 0 ${c//,/ } > $out/$a.json 2> $out/$a.err
       summary $out/$a.json "$a${c:+ [$c]}" ;;
     ll)
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $out/launches_$a.csv \
-        python bench.py --workload $a --points $b --steps 1 --warmup 3 --no-cpu-baseline --no-e2e ${c//,/ } > $out/ll_$a.log 2>&1
+        python bench.py --workload $a --points $b --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --sustained-steps 0 ${c//,/ } > $out/ll_$a.log 2>&1
       echo "launch list $a:"; shares $out/launches_$a.csv ;;
     ncu)
       timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"$c" -s ${d:-3} -c ${e:-1} -o $out/${a}_ncu -f \
-        python bench.py --workload $a --points $b --steps 1 --warmup 3 --no-cpu-baseline --no-e2e ${f//,/ } > $out/ncu_$a.log 2>&1
+        python bench.py --workload $a --points $b --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --sustained-steps 0 ${f//,/ } > $out/ncu_$a.log 2>&1
       echo "ncu $a exit $?" ;;
     sanitize)
       for tool in ${a:-memcheck racecheck initcheck synccheck}; do

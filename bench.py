@@ -124,7 +124,8 @@ def cpu_eval(oracle, w, vals, obs, nthreads):
     return oracle.interpn_regular(w.method, w.dims, w.starts, w.steps, vals, obs, linearize_extrapolation=w.linearize, nthreads=nthreads)
 
 
-def cpu_baseline(w, target_seconds: float, nthreads: int | None = None, steps: int = 1, warmup: int = 0, vals=None):
+def cpu_baseline(w, target_seconds: float, nthreads: int | None = None, steps: int = 1, warmup: int = 0, vals=None,
+                 max_points: int = 50_000_000):
     """Time the CPU oracle on a bounded sample of workload `w`; returns (points/s, info dict, seconds per pass)."""
     from oracle import oracle
 
@@ -137,10 +138,12 @@ def cpu_baseline(w, target_seconds: float, nthreads: int | None = None, steps: i
     t0 = time.perf_counter()
     cpu_eval(oracle, w, vals, obs, cores)
     rate = probe_n / max(time.perf_counter() - t0, 1e-6)
-    n = int(min(w.n_full, 50_000_000, max(probe_n, rate * target_seconds)))
+    n = int(min(w.n_full, max_points, max(probe_n, rate * target_seconds)))
     obs = w.queries(0, n, "np")
     for _ in range(warmup):
         cpu_eval(oracle, w, vals, obs, cores)
+    if steps == 1 and n / rate < 0.5 * target_seconds:  # the sample is capped: repeat it to fill the time
+        steps = int(min(50, max(1, target_seconds * rate / n)))
     times = []
     for _ in range(max(1, steps)):
         t0 = time.perf_counter()
@@ -160,15 +163,15 @@ def cpu_baseline(w, target_seconds: float, nthreads: int | None = None, steps: i
     return n / dt, info, dt
 
 
-def cpu_baseline_both(w, seconds: float, vals=None):
+def cpu_baseline_both(w, seconds: float, vals=None, max_points: int = 50_000_000):
     """All host cores (the headline CPU figure) and one thread — the reference's real execution model
     (multilinear/regular.rs:276-280: a serial loop, no threading anywhere in the crate)."""
     keys = ("value", "unit", "cores", "kind", "sample")
     if vals is None:
         vals = w.vals("np")
-    _, info, _ = cpu_baseline(w, seconds, vals=vals)
+    _, info, _ = cpu_baseline(w, seconds, vals=vals, max_points=max_points)
     res = {k: info[k] for k in keys}
-    _, one, _ = cpu_baseline(w, max(1.0, seconds / 2), nthreads=1, vals=vals)
+    _, one, _ = cpu_baseline(w, max(1.0, seconds / 2), nthreads=1, vals=vals, max_points=max_points)
     res["single_thread"] = {k: one[k] for k in keys}
     return res
 
@@ -667,7 +670,8 @@ def run_b200(args):
             if cx.rank == 0 and cx.world == 1 and not args.no_cpu_baseline:
                 wk = cx.W.get(name, np.float32 if dt == "f32" else np.float64)
                 try:
-                    r["cpu_baseline"] = cpu_baseline_both(wk, 1.5, vals=cx.last_vals if cx.last_vals is not None and cx.last_vals.size == wk.nvals else None)
+                    r["cpu_baseline"] = cpu_baseline_both(wk, 1.5, vals=cx.last_vals if cx.last_vals is not None and cx.last_vals.size == wk.nvals else None,
+                                                           max_points=4_000_000)  # generating the sample on the host dominates beyond that
                 except Exception as e:
                     r["cpu_baseline"] = {"error": repr(e)}
             suite.append(r)

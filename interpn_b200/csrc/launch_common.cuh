@@ -94,6 +94,9 @@ inline bool vector_aligned(const T* const* obs, int ndims, const T* out, int P) 
 #ifndef IB200_P_NEAREST_RECT
 #define IB200_P_NEAREST_RECT 2
 #endif
+#ifndef IB200_P_NEAREST_RECT_F32
+#define IB200_P_NEAREST_RECT_F32 4
+#endif
 #ifndef IB200_P_LINEAR_LO
 #define IB200_P_LINEAR_LO 4  // N <= 3
 #endif

@@ -10,7 +10,7 @@ cudaError_t launch_nearest(const DeviceGrid& g, const T* const* obs, size_t n, T
     // Points per thread: 4 on regular grids; 2 on rectilinear ones, whose twelve search chains per thread (3-D) cost
     // 78 registers and a quarter of the occupancy (measured: 3-D 78 -> 98 G points/s, 2-D 116 -> 120).
     // (f32 keeps 4: two floats per thread would halve the width of the streaming accesses, and its chains fit 64 registers)
-    constexpr int P = IB200_P_NEAREST, PR = sizeof(T) == 4 ? IB200_P_NEAREST : IB200_P_NEAREST_RECT;
+    constexpr int P = IB200_P_NEAREST, PR = sizeof(T) == 4 ? IB200_P_NEAREST_RECT_F32 : IB200_P_NEAREST_RECT;
     LaunchOpts popts;
     popts.points_per_thread = g.rect ? PR : P;
     const int pp = popts.points_per_thread;

@@ -25,8 +25,23 @@ namespace ib200 {
 
 constexpr int kSweepKeyDims = 3;
 constexpr int kSweepMaxBins = 4096;
-constexpr unsigned kSweepTile = 8192;       // histogram / scatter tile (16-bit tile-local indices)
-constexpr int kSweepScatterBlock = 1024;    // one scatter CTA per SM (its shared memory holds a whole tile)
+// Histogram / scatter tile (16-bit tile-local indices) and the scatter CTA. The scatter is a chain of shared-memory phases
+// separated by barriers with a DRAM round trip inside most of them, so what hides its latency is SEVERAL resident CTAs
+// per SM, not a big one (round 1: one CTA of 1024 threads on an 8192-point tile ran at 13 % issue activity,
+// profiles/r1_p5_c4_scatter_ncu.json).
+#ifndef IB200_SWEEP_TILE
+#define IB200_SWEEP_TILE 4096
+#endif
+#ifndef IB200_SWEEP_SCATTER_BLOCK
+#define IB200_SWEEP_SCATTER_BLOCK 512
+#endif
+#ifndef IB200_SWEEP_SCATTER_MINB
+#define IB200_SWEEP_SCATTER_MINB 3
+#endif
+constexpr unsigned kSweepTile = IB200_SWEEP_TILE;
+constexpr int kSweepScatterBlock = IB200_SWEEP_SCATTER_BLOCK;
+constexpr int kSweepScatterMinBlocks = IB200_SWEEP_SCATTER_MINB;
+static_assert(kSweepTile <= 65536 && kSweepTile % kSweepScatterBlock == 0, "16-bit tile-local indices, whole elements per thread");
 constexpr int kSweepSlots = 16;            // cursors per key: tile t uses slot t % 16 (same-address atomics serialise in L2)
 
 struct SweepKey {
@@ -135,7 +150,7 @@ struct SweepScatterArgs {
 // coalesced: every coordinate array of the tile is staged in shared memory (read in original order)
 // and written out in sorted order, consecutive threads to consecutive positions of a key's run.
 template <class T, int N>
-__global__ void __launch_bounds__(kSweepScatterBlock, 1) sweep_scatter_kernel(const __grid_constant__ SweepScatterArgs<T, N> s) {
+__global__ void __launch_bounds__(kSweepScatterBlock, kSweepScatterMinBlocks) sweep_scatter_kernel(const __grid_constant__ SweepScatterArgs<T, N> s) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* stage = reinterpret_cast<T*>(smem_raw);                       // [kSweepTile] one coordinate array of the tile
     unsigned* krank = reinterpret_cast<unsigned*>(stage + kSweepTile);  // [kSweepTile] key << 16 | rank, by tile-local index
@@ -428,7 +443,7 @@ inline cudaError_t launch_sweep(const DeviceGrid& g, int fp, int row_bytes_scale
             sa.orig = orig;
             sa.pos = pos;
             sa.nbins = key.nbins;
-            sweep_scatter_kernel<T, N><<<grid_for(tiles * kBlock, g.sm_count, 1), kSweepScatterBlock, scatter_smem, stream>>>(sa);
+            sweep_scatter_kernel<T, N><<<grid_for(tiles * kBlock, g.sm_count, kSweepScatterMinBlocks), kSweepScatterBlock, scatter_smem, stream>>>(sa);
             count_launch();
             count_launch();
             count_launch();

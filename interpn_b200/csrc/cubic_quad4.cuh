@@ -235,6 +235,17 @@ __device__ __forceinline__ void cubic_steps4(const T (&sub)[4][4], const QuadDim
     cubic_steps_rect<4, T>(sub, c, fl, all_none, out);
 }
 
+// Two steps (the stashed outer rows of a 4-D footprint are reduced two in-sector positions at a time).
+template <class T>
+__device__ __forceinline__ void cubic_steps2(const T (&u)[4][2], const QuadDim<T, false>& c, int fl, bool all_none, T (&out)[2]) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) out[j] = cubic_step_perm(u[0][j], u[1][j], u[2][j], u[3][j], c, fl, all_none);
+}
+template <class T>
+__device__ __forceinline__ void cubic_steps2(const T (&u)[4][2], const QuadDim<T, true>& c, int fl, bool all_none, T (&out)[2]) {
+    cubic_steps_rect<2, T>(u, c, fl, all_none, out);
+}
+
 // The same step on inputs in natural order: the permutation is done with selects (dimension N-2, whose four inputs
 // sit in one sector).
 template <class T, bool RECT>
@@ -360,36 +371,96 @@ __device__ __forceinline__ int cubic_perm_k(int mode, int k) {
 // in-sector positions at once; the rows of each dimension are visited in the permuted order of its saturation class.
 // The per-dimension parameters are read from the owner's slot (and the cell table) where they are used, so they are
 // live only for the steps of their dimension.
+// 16-byte vector of two T (f64: double2, f32: two pairs are wasted bandwidth-wise but keep one code path: float4 holds 4).
+template <class T> struct Stash2;
+template <> struct Stash2<double> { using V = double2; };
+template <> struct Stash2<float> { using V = float2; };
+
+#ifndef IB200_QUAD4_STASH
+#define IB200_QUAD4_STASH 1
+#endif
+// N = 4: the partial results of the outer row loop (four rows of dimension 1 x four in-sector positions = 16 values per
+// lane) are parked in shared memory instead of registers. With them in registers the 4-D kernels needed 122-128
+// registers (2 CTAs per SM, 24 % of the warps: profiles/r1_p5_x4_ncu.json) and sat on load latency; per-thread columns
+// of `stash` ([8 vectors of two values][kBlock threads], consecutive threads in consecutive vectors: conflict-free).
+constexpr bool kQuad4Stash = IB200_QUAD4_STASH != 0;
+#ifndef IB200_QUAD4_INNER2
+#define IB200_QUAD4_INNER2 0
+#endif
+constexpr bool kQuad4Inner2 = IB200_QUAD4_INNER2 != 0;
+
 template <int D, class T, int N, bool RECT>
 __device__ __forceinline__ void quad4_rows(const EvalArgs<T, N>& a, const T* __restrict__ axes, int idx,
-                                           const QuadSlot<T, N, RECT>* sp, int flags, unsigned none_mask, T (&out)[4]) {
+                                           const QuadSlot<T, N, RECT>* sp, int flags, unsigned none_mask,
+                                           typename Stash2<T>::V* __restrict__ stash, T (&out)[4]) {
     if constexpr (D == 0) {
         load_row<T, 4, true, int>(nullptr, a.win, idx, out);
     } else {
         const int fl = flags >> (4 * (D - 1));
         const bool all_none = (none_mask >> (D - 1)) & 1u;
         const int mode = all_none ? 0 : (fl & 3), stride = a.istride[D - 1];
-        T sub[4][4];
-        if constexpr (D >= 2) {
-            // Not unrolled (code size: a 4-D footprint unrolled 16 ways did not fit the instruction cache). The four
-            // partial rows are shifted through `sub` so that no register array is indexed dynamically.
+        if constexpr (D >= 2 && kQuad4Stash) {
+            using V = typename Stash2<T>::V;
+            // Not unrolled (code size: a 4-D footprint unrolled 16 ways did not fit the instruction cache).
 #pragma unroll(kQuad4UnrollK)
             for (int k = 0; k < 4; ++k) {
                 T rk[4];
-                quad4_rows<D - 1, T, N, RECT>(a, axes, idx + cubic_perm_k(mode, k) * stride, sp, flags, none_mask, rk);
+                quad4_rows<D - 1, T, N, RECT>(a, axes, idx + cubic_perm_k(mode, k) * stride, sp, flags, none_mask, stash, rk);
+                V lo, hi;
+                lo.x = rk[0]; lo.y = rk[1]; hi.x = rk[2]; hi.y = rk[3];
+                stash[(2 * k) * kBlock] = lo;
+                stash[(2 * k + 1) * kBlock] = hi;
+            }
+            const QuadDim<T, RECT> c = quad4_dim<T, N>(a, axes, sp, D - 1);
+            // two in-sector positions at a time: half the live inputs and temporaries of four interleaved steps
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    sub[0][j] = sub[1][j]; sub[1][j] = sub[2][j]; sub[2][j] = sub[3][j]; sub[3][j] = rk[j];
+            for (int h = 0; h < 2; ++h) {
+                T u[4][2];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const V v = stash[(2 * k + h) * kBlock];
+                    u[k][0] = v.x; u[k][1] = v.y;
                 }
+                T o2[2];
+                if (all_none) cubic_steps2(u, c, fl, true, o2);
+                else cubic_steps2(u, c, fl, false, o2);
+                out[2 * h] = o2[0]; out[2 * h + 1] = o2[1];
             }
         } else {
+            T sub[4][4];
+            if constexpr (D >= 2) {
+                // The four partial rows are shifted through `sub` so that no register array is indexed dynamically.
+#pragma unroll(kQuad4UnrollK)
+                for (int k = 0; k < 4; ++k) {
+                    T rk[4];
+                    quad4_rows<D - 1, T, N, RECT>(a, axes, idx + cubic_perm_k(mode, k) * stride, sp, flags, none_mask, stash, rk);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                quad4_rows<D - 1, T, N, RECT>(a, axes, idx + cubic_perm_k(mode, k) * stride, sp, flags, none_mask, sub[k]);
+                    for (int j = 0; j < 4; ++j) {
+                        sub[0][j] = sub[1][j]; sub[1][j] = sub[2][j]; sub[2][j] = sub[3][j]; sub[3][j] = rk[j];
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    quad4_rows<D - 1, T, N, RECT>(a, axes, idx + cubic_perm_k(mode, k) * stride, sp, flags, none_mask, stash, sub[k]);
+            }
+            const QuadDim<T, RECT> c = quad4_dim<T, N>(a, axes, sp, D - 1);
+            if constexpr (N >= 4 && kQuad4Inner2) {
+                // 4-D: two steps at a time (fewer live temporaries; the kernel is bound by registers, not by ILP)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    T u[4][2], o2[2];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { u[k][0] = sub[k][2 * h]; u[k][1] = sub[k][2 * h + 1]; }
+                    if (all_none) cubic_steps2(u, c, fl, true, o2);
+                    else cubic_steps2(u, c, fl, false, o2);
+                    out[2 * h] = o2[0]; out[2 * h + 1] = o2[1];
+                }
+            } else {
+                if (all_none) cubic_steps4(sub, c, fl, true, out);  // one warp-uniform branch around the four independent steps
+                else cubic_steps4(sub, c, fl, false, out);
+            }
         }
-        const QuadDim<T, RECT> c = quad4_dim<T, N>(a, axes, sp, D - 1);
-        if (all_none) cubic_steps4(sub, c, fl, true, out);  // one warp-uniform branch around the four independent steps
-        else cubic_steps4(sub, c, fl, false, out);
     }
 }
 
@@ -398,9 +469,14 @@ __host__ __device__ constexpr int quad4_slot_warp_bytes() {  // one slot per lan
     return 32 * static_cast<int>(sizeof(QuadSlot<T, N, RECT>)) + 8 * 16;
 }
 constexpr int kQuad4XposeQuad = 20;  // transposition buffer [quad][lane j][point p]: quad stride 16 + 4 elements
+template <class T, int N>
+__host__ __device__ constexpr size_t quad4_stash_bytes() {  // eight 2-element vectors per thread, N = 4 only
+    return (N >= 4 && kQuad4Stash) ? static_cast<size_t>(kBlock) * 8 * 2 * sizeof(T) : 0;
+}
 template <class T, int N, bool RECT>
 __host__ __device__ constexpr size_t quad4_smem_bytes() {  // beyond the staged axes
-    return static_cast<size_t>(kBlock / 32) * (quad4_slot_warp_bytes<T, N, RECT>() + 8 * kQuad4XposeQuad * sizeof(T));
+    return static_cast<size_t>(kBlock / 32) * (quad4_slot_warp_bytes<T, N, RECT>() + 8 * kQuad4XposeQuad * sizeof(T)) +
+           quad4_stash_bytes<T, N>();
 }
 
 template <class T, int N, bool RECT, int MINB>
@@ -427,6 +503,8 @@ __global__ void __launch_bounds__(kBlock, MINB) cubic_quad4_kernel(const __grid_
     Slot* myslot = reinterpret_cast<Slot*>(wslots) + lane;
     const Slot* qslots = reinterpret_cast<const Slot*>(wslots) + (lane & ~3u);
     T* xq = s_xpose + (warp * 8 + quad) * kQuad4XposeQuad;
+    // per-thread column of the stash (16-byte aligned: every region before it is a multiple of 16 bytes)
+    typename Stash2<T>::V* stash = reinterpret_cast<typename Stash2<T>::V*>(s_xpose + kWarps * 8 * kQuad4XposeQuad) + threadIdx.x;
 
     // The coordinates of the NEXT block of points are requested after the last gather of the current one has been
     // consumed (its registers are free again), so their DRAM latency overlaps the transposition, the final step
@@ -461,7 +539,7 @@ __global__ void __launch_bounds__(kBlock, MINB) cubic_quad4_kernel(const __grid_
 #pragma unroll
             for (int d = 0; d < N; ++d) none_mask |= (edges[d] & (0x11111111u << p)) == 0u ? (1u << d) : 0u;
             T r[4];
-            quad4_rows<N - 2, T, N, RECT>(a, axes, sp->base + static_cast<int>(b), sp, flags, none_mask, r);
+            quad4_rows<N - 2, T, N, RECT>(a, axes, sp->base + static_cast<int>(b), sp, flags, none_mask, stash, r);
             const QuadDim<T, RECT> c = quad4_dim<T, N>(a, axes, sp, N - 2);
             xq[b * 4 + p] = cubic_step_sel<T, RECT>(r[0], r[1], r[2], r[3], c, flags >> (4 * (N - 2)), (none_mask >> (N - 2)) & 1u);
         }

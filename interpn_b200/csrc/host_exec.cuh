@@ -24,109 +24,11 @@
 #include <string>
 #include <thread>
 
+#include "copy_pool.h"
+
 namespace ib200 {
 
 size_t sweep_env_common(const char* name, size_t fallback);  // launch_misc.cu
-
-// ---------------------------------------------------------------------------------------------------------------------
-// Host threads that move pageable memory to / from pinned staging. A copy is cut into 1 MiB pieces; the calling thread
-// works on its own pieces too, so the pool never deadlocks and a pool of zero threads still copies.
-// ---------------------------------------------------------------------------------------------------------------------
-class CopyPool {
-public:
-    static CopyPool& get() {
-        static CopyPool pool;
-        return pool;
-    }
-    int threads() const { return static_cast<int>(workers_.size()); }
-
-    void copy(void* dst, const void* src, size_t bytes) {
-        constexpr size_t kPiece = size_t(1) << 20;
-        if (bytes <= 2 * kPiece || workers_.empty()) {
-            memcpy(dst, src, bytes);
-            return;
-        }
-        Job job;
-        job.dst = static_cast<char*>(dst);
-        job.src = static_cast<const char*>(src);
-        job.bytes = bytes;
-        job.pieces = (bytes + kPiece - 1) / kPiece;
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            jobs_.push_back(&job);
-        }
-        cv_.notify_all();
-        work_on(job);  // the caller takes pieces as well
-        {
-            std::lock_guard<std::mutex> lk(mu_);  // nobody may pick the job up any more
-            jobs_.erase(std::remove(jobs_.begin(), jobs_.end(), &job), jobs_.end());
-        }
-        while (job.done.load(std::memory_order_acquire) != job.pieces || job.users.load(std::memory_order_acquire) != 0)
-            std::this_thread::yield();
-    }
-
-private:
-    struct Job {
-        char* dst;
-        const char* src;
-        size_t bytes, pieces;
-        std::atomic<size_t> next{0}, done{0};
-        std::atomic<int> users{0};  // pool threads currently inside work_on(this job)
-    };
-    static void work_on(Job& j) {
-        constexpr size_t kPiece = size_t(1) << 20;
-        for (;;) {
-            const size_t p = j.next.fetch_add(1, std::memory_order_relaxed);
-            if (p >= j.pieces) return;
-            const size_t lo = p * kPiece, len = std::min(kPiece, j.bytes - lo);
-            memcpy(j.dst + lo, j.src + lo, len);
-            j.done.fetch_add(1, std::memory_order_release);
-        }
-    }
-    CopyPool() {
-        int n = 0;
-        if (const char* e = getenv("INTERPN_B200_COPY_THREADS")) n = atoi(e);
-        else {
-            const int hw = static_cast<int>(std::thread::hardware_concurrency());
-            n = std::max(1, std::min(12, hw / 2)) - 1;  // the calling thread is one of the copiers
-        }
-        for (int i = 0; i < n; ++i) workers_.emplace_back([this] { loop(); });
-    }
-    ~CopyPool() {
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            stop_ = true;
-        }
-        cv_.notify_all();
-        for (auto& t : workers_) t.join();
-    }
-    void loop() {
-        std::unique_lock<std::mutex> lk(mu_);
-        for (;;) {
-            Job* j = nullptr;
-            cv_.wait(lk, [&] {
-                if (stop_) return true;
-                for (Job* k : jobs_)
-                    if (k->next.load(std::memory_order_relaxed) < k->pieces) {
-                        j = k;
-                        return true;
-                    }
-                return false;
-            });
-            if (stop_) return;
-            j->users.fetch_add(1, std::memory_order_relaxed);  // under the lock: the owner cannot have removed the job yet
-            lk.unlock();
-            work_on(*j);
-            j->users.fetch_sub(1, std::memory_order_release);
-            lk.lock();
-        }
-    }
-    std::mutex mu_;
-    std::condition_variable cv_;
-    std::deque<Job*> jobs_;
-    std::vector<std::thread> workers_;
-    bool stop_ = false;
-};
 
 // True when `p` is page-locked memory the GPU can DMA from/to in place (cudaHostAlloc, cudaHostRegister, managed).
 inline bool host_pointer_is_pinned(const void* p) {
@@ -326,13 +228,14 @@ int run_host_batch(DeviceSlots* const* devs, int ndev, const void* const* in_hos
             Slot& s = D.slot[si];
             const size_t lo = c * chunk, cnt = std::min(chunk, n - lo);
             inflight.emplace_back(c, si);  // from here on the chunk must be retired, whatever happens
+            if (stage_in) {
+                // the slot's previous H2D from these staging buffers finished before its kernel, i.e. before it retired
+                const void* srcs[kMaxNd];
+                for (int j = 0; j < nin; ++j) srcs[j] = static_cast<const char*>(in_host[j]) + lo * elem;
+                pool->copy_many(nin, s.hin, srcs, cnt * elem);
+            }
             for (int j = 0; j < nin; ++j) {
-                const char* src = static_cast<const char*>(in_host[j]) + lo * elem;
-                if (stage_in) {
-                    // the slot's previous H2D from this staging buffer finished before its kernel, i.e. before it retired
-                    pool->copy(s.hin[j], src, cnt * elem);
-                    src = static_cast<const char*>(s.hin[j]);
-                }
+                const char* src = stage_in ? static_cast<const char*>(s.hin[j]) : static_cast<const char*>(in_host[j]) + lo * elem;
                 CUDA_TRY(cudaMemcpyAsync(s.in[j], src, cnt * elem, cudaMemcpyHostToDevice, s.stream));
             }
             CUDA_TRY(cudaMemsetAsync(s.flag_dev, 0xff, sizeof(unsigned long long), s.stream));

@@ -47,6 +47,7 @@ cudaError_t launch_cubic_rect(const DeviceGrid& g, const T* const* obs, size_t n
                         break;
                     case 4:
                         if (minb == 3) e = q4(cubic_quad4_kernel<T, 4, true, 3>, integral_constant<int, 4>());
+                        else if (minb == 4) e = q4(cubic_quad4_kernel<T, 4, true, 4>, integral_constant<int, 4>());
                         else if (minb == 1) e = q4(cubic_quad4_kernel<T, 4, true, 1>, integral_constant<int, 4>());
                         else e = q4(cubic_quad4_kernel<T, 4, true, 2>, integral_constant<int, 4>());
                         break;

@@ -27,16 +27,17 @@ constexpr int kSweepKeyDims = 3;
 constexpr int kSweepMaxBins = 4096;
 // Histogram / scatter tile (16-bit tile-local indices) and the scatter CTA. The scatter is a chain of shared-memory phases
 // separated by barriers with a DRAM round trip inside most of them, so what hides its latency is SEVERAL resident CTAs
-// per SM, not a big one (round 1: one CTA of 1024 threads on an 8192-point tile ran at 13 % issue activity,
-// profiles/r1_p5_c4_scatter_ncu.json).
+// per SM, not a big one? Measured (round 2, gpurun_out/r2_exp1): NO — 8192-point tiles on one 1024-thread CTA per SM
+// (C4 7.95 G points/s) beat 4096/512 x3 (7.27), 4096/1024 x2 (7.59) and 2048/256 x6 (6.48): smaller tiles shorten the
+// runs of a (tile, key) pair (C4: 529 keys, 15 points per run at 8192) and that costs more than the extra overlap buys.
 #ifndef IB200_SWEEP_TILE
-#define IB200_SWEEP_TILE 4096
+#define IB200_SWEEP_TILE 8192
 #endif
 #ifndef IB200_SWEEP_SCATTER_BLOCK
-#define IB200_SWEEP_SCATTER_BLOCK 512
+#define IB200_SWEEP_SCATTER_BLOCK 1024
 #endif
 #ifndef IB200_SWEEP_SCATTER_MINB
-#define IB200_SWEEP_SCATTER_MINB 3
+#define IB200_SWEEP_SCATTER_MINB 1
 #endif
 constexpr unsigned kSweepTile = IB200_SWEEP_TILE;
 constexpr int kSweepScatterBlock = IB200_SWEEP_SCATTER_BLOCK;

@@ -365,6 +365,19 @@ int rect_new(int method, const T* const* grids, const size_t* grid_lens, size_t 
             }
         }
     }
+    // The bucket tables index with (x - g0) * (buckets / span) evaluated in T (kernels.cuh rect_lower_bound,
+    // rect_cell_locate): the span and the scale must be finite, normal numbers IN T, or a computed bucket can land
+    // arbitrarily far from the true one (f32 axes spanning more than FLT_MAX, or a subnormal span). Such axes keep the
+    // plain bisection, like axes that are not strictly increasing.
+    for (size_t d = 0; d < ngrids && sorted; ++d) {
+        const size_t n = grid_lens[d];
+        volatile T span_t = grids[d][n - 1] - grids[d][0];
+        const double span = static_cast<double>(grids[d][n - 1]) - static_cast<double>(grids[d][0]);
+        const double tmin = sizeof(T) == 8 ? 0x1p-1022 : 0x1p-126, tmax = sizeof(T) == 8 ? 0x1p1023 : 0x1p127;
+        const double scale_hi = static_cast<double>(4 * n > 65536 ? 65536 : 4 * n) / span, scale_lo = 2.0 / span;
+        const double st = static_cast<double>(span_t);
+        if (!(st - st == 0.0) || !(st >= tmin) || !(scale_hi < tmax) || !(scale_lo >= tmin)) sorted = false;
+    }
     g.rect_fast = sorted ? 1 : 0;
     g.rect_fast_div = sorted && widths_ok ? 1 : 0;
     if (sorted) {
@@ -608,6 +621,12 @@ int eval_device(interpn_b200_interp* h, const T* const* obs, size_t nobs, size_t
     if (nobs != static_cast<size_t>(h->g.ndims)) return INTERPN_B200_ERR_DIM_MISMATCH;
     if (n == 0) return INTERPN_B200_OK;
     if (!out) return INTERPN_B200_ERR_INVALID_ARG;
+    int cur = -1;
+    CUDA_TRY(cudaGetDevice(&cur));
+    if (cur != h->device) {  // the grid, the stream and the buffers all belong to the interpolator's device
+        snprintf(t_detail, sizeof(t_detail), "interpolator lives on device %d but device %d is current", h->device, cur);
+        return INTERPN_B200_ERR_INVALID_ARG;
+    }
     CUDA_TRY(launch_eval<T>(h->g, obs, n, out, h->first_bad_dev, 0ull, static_cast<cudaStream_t>(stream)));
     return INTERPN_B200_OK;
 }

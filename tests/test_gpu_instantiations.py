@@ -265,3 +265,31 @@ def test_check_bounds_at_scale(ib, oracle, dtype):
     obs[1][9_999_999] = -np.inf
     obs[2][0] = np.inf
     both(obs, [False, True, True])
+
+
+# ------------------------------------------------------------------------------------------------ extreme axes
+@pytest.mark.parametrize("method", ["linear", "cubic", "nearest"])
+@pytest.mark.parametrize("kind", ["huge_span", "subnormal_span"])
+def test_rectilinear_axes_whose_span_leaves_the_bucket_tables_range(ib, oracle, method, kind):
+    """f32 axes that are strictly increasing and finite, but whose span overflows (or is subnormal) in f32: the bucket
+    tables of the rectilinear search would compute garbage buckets, so such grids must take the plain bisection and still
+    match the reference bit for bit (capi.cu rect_new)."""
+    rng = np.random.default_rng(12)
+    n = 20000
+    if kind == "huge_span":
+        ax = np.linspace(-3.0e38, 3.0e38, 9).astype(np.float32)
+        q = (rng.random(n) * 6.4e38 - 3.2e38).astype(np.float32)
+    else:
+        ax = (np.arange(9, dtype=np.float64) * 3e-43).astype(np.float32)  # subnormal nodes, subnormal span
+        q = (rng.random(n) * 2.6e-42 - 1e-43).astype(np.float32)
+    assert np.all(np.diff(ax.astype(np.float64)) > 0) and np.all(np.isfinite(ax))
+    grids = [ax, np.linspace(0.0, 1.0, 6).astype(np.float32)]
+    vals = rng.standard_normal(9 * 6).astype(np.float32)
+    obs = [q, rng.random(n).astype(np.float32) * 1.2 - 0.1]
+    obs[0][:9] = ax
+    extra = (True,) if method == "cubic" else ()
+    out = np.zeros(n, dtype=np.float32)
+    getattr(ib.raw, f"interpn_{method}_rectilinear_f32")(grids, vals, *extra, obs, out)
+    want = oracle.interpn_rectilinear(method, grids, vals, obs, linearize_extrapolation=True, nthreads=4)
+    both_nan = np.isnan(out) & np.isnan(want)
+    assert np.all((out.view(np.uint32) == want.view(np.uint32)) | both_nan)

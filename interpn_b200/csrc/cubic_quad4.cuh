@@ -388,10 +388,9 @@ constexpr bool kQuad4Stash = IB200_QUAD4_STASH != 0;
 #define IB200_QUAD4_INNER2 0
 #endif
 constexpr bool kQuad4Inner2 = IB200_QUAD4_INNER2 != 0;
-#ifndef IB200_QUAD4_PREFETCH
-#define IB200_QUAD4_PREFETCH 0
-#endif
-constexpr bool kQuad4Prefetch = IB200_QUAD4_PREFETCH != 0;
+// Measured and dropped (round 2, gpurun_out/r2_exp3, commit "prefetch variant"): issuing the four sector loads of row
+// k+1 before the steps of row k from a second register block (software pipeline, 128 registers with ~150 bytes of
+// spills) ran 4-D regular 32^4 at 4.65 instead of 6.49 G points/s and 4-D rectilinear 32^4 at 1.51 instead of 2.37.
 
 template <int D, class T, int N, bool RECT>
 __device__ __forceinline__ void quad4_rows(const EvalArgs<T, N>& a, const T* __restrict__ axes, int idx,
@@ -403,59 +402,7 @@ __device__ __forceinline__ void quad4_rows(const EvalArgs<T, N>& a, const T* __r
         const int fl = flags >> (4 * (D - 1));
         const bool all_none = (none_mask >> (D - 1)) & 1u;
         const int mode = all_none ? 0 : (fl & 3), stride = a.istride[D - 1];
-        if constexpr (D == 2 && kQuad4Stash && kQuad4Prefetch) {
-            // Software pipeline over the four rows of dimension 1: the four sector loads of row k+1 are issued before the
-            // steps of row k, ping-ponging between two register blocks (no moves); the partial results go to the stash.
-            using V = typename Stash2<T>::V;
-            const int fl0 = flags;
-            const bool none0 = none_mask & 1u;
-            const int mode0 = none0 ? 0 : (fl0 & 3), stride0 = a.istride[0];
-            auto load4 = [&](int k, T (&blk)[4][4]) {
-                const int base = idx + cubic_perm_k(mode, k) * stride;
-#pragma unroll
-                for (int m = 0; m < 4; ++m) load_row<T, 4, true, int>(nullptr, a.win, base + cubic_perm_k(mode0, m) * stride0, blk[m]);
-            };
-            auto reduce0 = [&](const T (&blk)[4][4], int k) {
-                const QuadDim<T, RECT> c0 = quad4_dim<T, N>(a, axes, sp, 0);
-                T rk[4];
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    T u[4][2], o2[2];
-#pragma unroll
-                    for (int m = 0; m < 4; ++m) { u[m][0] = blk[m][2 * h]; u[m][1] = blk[m][2 * h + 1]; }
-                    if (none0) cubic_steps2(u, c0, fl0, true, o2);
-                    else cubic_steps2(u, c0, fl0, false, o2);
-                    rk[2 * h] = o2[0]; rk[2 * h + 1] = o2[1];
-                }
-                V lo, hi;
-                lo.x = rk[0]; lo.y = rk[1]; hi.x = rk[2]; hi.y = rk[3];
-                stash[(2 * k) * kBlock] = lo;
-                stash[(2 * k + 1) * kBlock] = hi;
-            };
-            T blkA[4][4], blkB[4][4];
-            load4(0, blkA);
-#pragma unroll 1
-            for (int k = 0; k < 4; k += 2) {
-                load4(k + 1, blkB);
-                reduce0(blkA, k);
-                if (k + 2 < 4) load4(k + 2, blkA);
-                reduce0(blkB, k + 1);
-            }
-            const QuadDim<T, RECT> c = quad4_dim<T, N>(a, axes, sp, D - 1);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                T u[4][2];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const V v = stash[(2 * k + h) * kBlock];
-                    u[k][0] = v.x; u[k][1] = v.y;
-                }
-                T o2[2];
-                if (all_none) cubic_steps2(u, c, fl, true, o2);
-                else cubic_steps2(u, c, fl, false, o2);
-                out[2 * h] = o2[0]; out[2 * h + 1] = o2[1];
-            }
-        } else if constexpr (D >= 2 && kQuad4Stash) {
+        if constexpr (D >= 2 && kQuad4Stash) {
             using V = typename Stash2<T>::V;
             // Not unrolled (code size: a 4-D footprint unrolled 16 ways did not fit the instruction cache).
 #pragma unroll(kQuad4UnrollK)

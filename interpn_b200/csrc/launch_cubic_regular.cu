@@ -46,9 +46,11 @@ cudaError_t launch_cubic_regular(const DeviceGrid& g, const T* const* obs, size_
                         else e = q4(cubic_quad4_kernel<T, 3, false, 4>, integral_constant<int, 3>());
                         break;
                     case 4:
-                        if (minb == 3) e = q4(cubic_quad4_kernel<T, 4, false, 3>, integral_constant<int, 4>());
+                        // 80 registers / 3 CTAs per SM now that the outer partial rows live in shared memory (cubic_quad4.cuh
+                        // stash): 6.68 against 6.49 (2 CTAs) and 5.00 (4 CTAs, spills) G points/s on 32^4, gpurun_out/r2_exp2
+                        if (minb == 2) e = q4(cubic_quad4_kernel<T, 4, false, 2>, integral_constant<int, 4>());
                         else if (minb == 4) e = q4(cubic_quad4_kernel<T, 4, false, 4>, integral_constant<int, 4>());
-                        else e = q4(cubic_quad4_kernel<T, 4, false, 2>, integral_constant<int, 4>());
+                        else e = q4(cubic_quad4_kernel<T, 4, false, 3>, integral_constant<int, 4>());
                         break;
                     default: break;
                 }

@@ -1,0 +1,35 @@
+#!/bin/bash
+# Round-2 profile session (one GPU, under gpurun): DRAM traffic per step of every bench workload (metrics-only ncu pass),
+# launch lists, and ncu --set full captures of the dominant kernels. Output: gpurun_out/r2_prof/. Summaries are made
+# on the build machine with tools/ncu_summary.py / tools/traffic_table.py and copied to profiles/.
+out=gpurun_out/r2_prof; mkdir -p $out
+B="--steps 1 --warmup 3 --no-cpu-baseline --no-e2e --sustained-steps 0"
+traffic() { # workload dtype points
+  timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+    --log-file $out/traffic_$1_$2.csv python bench.py --workload $1 --dtype $2 --points $3 $B > $out/traffic_$1_$2.log 2>&1
+  echo "traffic $1 $2 exit $?"
+}
+traffic c2_cubic3d_reg100 f64 100000000
+traffic c1_linear3d_reg20 f64 1000000
+traffic c3_linear4d_rect64 f64 100000000
+traffic c3_cubic4d_rect64 f64 100000000
+traffic c4_linear6d_reg24 f64 125000000
+for w in c5_nearest2d_reg1024 c5_nearest3d_reg128 c5_nearest2d_rect1024 c5_nearest3d_rect128; do
+  traffic $w f64 200000000; traffic $w f32 200000000
+done
+# launch list of the headline command itself (suite off: the timed region of the default line)
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 400 --csv --log-file $out/launches_default_bench.csv \
+  python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e --sustained-steps 0 --suite none > $out/launches_default_bench.log 2>&1; echo "launch list exit $?"
+full() { # name workload dtype points kernel-regex skip count
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"$5" -s $6 -c $7 -o $out/$1 -f \
+    python bench.py --workload $2 --dtype $3 --points $4 $B > $out/full_$1.log 2>&1; echo "ncu full $1 exit $?"
+}
+full c2_quad4 c2_cubic3d_reg100 f64 100000000 cubic_quad4 3 1
+full x4reg_quad4 x_cubic4d_reg32 f64 50000000 cubic_quad4 3 1
+full c3c_quad4 c3_cubic4d_rect64 f64 100000000 cubic_quad4 3 1
+full c3l_slab c3_linear4d_rect64 f64 100000000 linear_slab 9 3
+full c4_eval c4_linear6d_reg24 f64 125000000 linear_kernel 3 1
+full c4_unsort c4_linear6d_reg24 f64 125000000 sweep_unsort 3 1
+full c5_n2rect_f32 c5_nearest2d_rect1024 f32 200000000 nearest_kernel 3 1
+full c5_n2rect_f64 c5_nearest2d_rect1024 f64 200000000 nearest_kernel 3 1
+ls -la $out | tail -n 40

@@ -160,7 +160,9 @@ int window_width(const DeviceGrid& g) {
         const size_t b = g.nvals * static_cast<size_t>(g.elem);
         w = (g.ndims >= 2 && !(g.ndims <= 4 && b > (48u << 10) && b <= (100u << 10))) ? 4 : 2;
     }
-    if (g.method == INTERPN_B200_CUBIC && g.ndims <= 4) w = 4;
+    // cubic N = 1: rows of four; N = 2..4: the coefficient layout (cubic_quad4.cuh), which on rectilinear axes is built from
+    // the per-cell constant table and therefore exists only for strictly increasing finite axes
+    if (g.method == INTERPN_B200_CUBIC && g.ndims <= 4 && !(g.rect && g.ndims >= 2 && !g.rect_cubic_table)) w = 4;
     if (!w) return 0;
     // Kept up to 8 GiB and a quarter of the free memory. Direct kernels gather from it only while it is
     // L2-resident (<= 64 MB, launch_common.cuh kWindowL2Bytes); beyond that it serves the bin-swept path
@@ -170,10 +172,11 @@ int window_width(const DeviceGrid& g) {
     const size_t bytes = g.nvals * static_cast<size_t>(g.elem);
     size_t min_kb = 0;  // even L1-resident grids gain: half (linear) or a quarter (cubic) as many load instructions
     if (const char* e = getenv("INTERPN_B200_WINDOW_MIN_KB")) min_kb = static_cast<size_t>(strtoull(e, nullptr, 10));
-    if (bytes < (min_kb << 10) || bytes * w > (max_mb << 20)) return 0;
-    if (bytes * w > (size_t(64) << 20)) {
+    const size_t wbytes = window_elems(g, w) * static_cast<size_t>(g.elem);
+    if (bytes < (min_kb << 10) || wbytes > (max_mb << 20)) return 0;
+    if (wbytes > (size_t(64) << 20)) {
         size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || bytes * w > free_b / 4) return 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || wbytes > free_b / 4) return 0;
     }
     return w;
 }
@@ -183,9 +186,10 @@ int upload_vals(interpn_b200_interp* h, const void* vals, int vals_location) {
     const size_t bytes = g.nvals * static_cast<size_t>(g.elem);
     CUDA_TRY(cudaMalloc(&g.vals, bytes ? bytes : 1));
     g.win_width = window_width(g);
-    // cubic N = 2..4: cross-window layout (quad-cooperative kernels); linear N >= 2: patch layout
+    // cubic N = 2..4: coefficient layout (quad-cooperative kernels); linear N >= 2: patch layout
     g.win_cross = g.win_width == 4 && g.ndims >= 2;
-    if (g.win_width) CUDA_TRY(cudaMalloc(&g.win, bytes * g.win_width));
+    g.win_bytes = window_elems(g, g.win_width) * static_cast<size_t>(g.elem);
+    if (g.win_width) CUDA_TRY(cudaMalloc(&g.win, g.win_bytes));
     if (vals_location == INTERPN_B200_VALS_UNINIT) return INTERPN_B200_OK;
     if (!vals) return INTERPN_B200_ERR_INVALID_ARG;
     CUDA_TRY(cudaMemcpy(g.vals, vals, bytes,
@@ -547,8 +551,8 @@ int ensure_replicas(interpn_b200_interp* h, int want) {
         CUDA_TRY(cudaMalloc(&r->g.vals, bytes ? bytes : 1));
         CUDA_TRY(cudaMemcpyPeer(r->g.vals, dev, g.vals, h->device, bytes));
         if (g.win) {
-            CUDA_TRY(cudaMalloc(&r->g.win, bytes * g.win_width));
-            CUDA_TRY(cudaMemcpyPeer(r->g.win, dev, g.win, h->device, bytes * g.win_width));
+            CUDA_TRY(cudaMalloc(&r->g.win, g.win_bytes));
+            CUDA_TRY(cudaMemcpyPeer(r->g.win, dev, g.win, h->device, g.win_bytes));
         }
         if (g.axes) {
             CUDA_TRY(cudaMalloc(&r->g.axes, static_cast<size_t>(g.axes_total) * g.elem));

@@ -1,34 +1,40 @@
-// cubic_quad4.cuh — multicubic N = 2..4 on a regular grid, second generation of the quad-cooperative kernel
-// (kernels.cuh cubic_quad_kernel): a quad of four lanes evaluates FOUR query points per iteration.
+// cubic_quad4.cuh — multicubic N = 2..4, third generation: a quad of four lanes evaluates FOUR query points per
+// iteration over the COEFFICIENT layout of the grid.
 //
-// Why (profiles/r1_p4_c2_quad_ncu.json): the one-point-per-quad kernel executes 360 warp instructions per 8 points,
-// only 130 of them FP64 — every lane repeats the final 1-D step of its quad (3 of 4 wasted), one lane in four
-// repeats a cell location, parameters travel by 20 shuffles per point, and the five-way saturation switch costs
-// 16 selects per 1-D step whenever one lane of the warp is near an edge. Here
+// First-level hoisting. The reference reduces a 4^N footprint dimension 0 first (multicubic/regular.rs:368-412: vertex
+// i's offset along dimension k is bit field k of i), so 4^(N-1) of the (4^N - 1)/3 one-dimensional steps of a point —
+// 16 of 21 in 3-D, 64 of 85 in 4-D — take four RAW grid values along dimension 0. Everything such a step computes before
+// its Horner polynomial (the differences, the centred / non-uniform slopes with their two IEEE quotients on rectilinear
+// axes, the natural-spline end slope, the coefficients c1, c2, c3 of normalized_hermite_spline, multicubic/mod.rs:72-91)
+// depends on the grid values and on the CELL of dimension 0 only, not on t. It is therefore computed once per
+// (cell of dimension 0, node of the other dimensions) when the interpolator is built — by cubic_coef_perm below, the
+// same IEEE operations in the same order as the step itself — and stored as one 32-byte sector (y0, c1, c2, c3):
+//   cwin[(slot * S0 + r) * 4 + 0..3],  r = flat index over dimensions 1..N-1,  S0 = stride of dimension 0,
+//   slot 1 + c for cell c = clamp(floor index, 0, dim0 - 2) (cell 0 = low end class, dim0 - 2 = high end class),
+//   slot 0 / dim0 = (y1, k1, 0, 0) of the linearized extrapolation below / above the grid.
+// A first-level step is then ONE sector load and three multiply-adds (6 FP64 instructions; 3 in the fma flavour)
+// instead of four loads and 14 (regular) or 30 (rectilinear) instructions, bit for bit the reference's result. The
+// table is the size of the former four-fold cross-window copy (x (dim0 + 1)/dim0).
+//
+// Work split (unchanged from the second generation, profiles/r1_p5_c2_quad4_ncu.json):
 //   * thread i OWNS point i: it loads the point's coordinates (coalesced), locates it on every dimension with the
 //     division-free test of device_math.cuh (the FMA remainder proves floor((x-start)/step); rare points take the
 //     IEEE division), evaluates the point's LAST 1-D step and stores the result (coalesced);
-//   * in between, the quad works through its four points one after the other: lane j gathers the sector of
-//     last-dimension node j from the cross-window layout (one LDG.256 brings four consecutive nodes of dimension
-//     N-2) and reduces dimensions 0..N-2 on it;
+//   * in between, the quad works through its four points one after the other: lane j reduces dimensions 0..N-2 at
+//     last-dimension node j — sectors of consecutive last-dimension nodes are adjacent, so a quad's load is 128
+//     contiguous bytes;
 //   * parameters (t per dimension, flat index, saturation flags) and the 4x4 transposition of the partial results
-//     go through padded shared memory (two LDS.128 per point instead of 20 shuffles; conflict-free strides);
-//   * the saturation switch becomes a PERMUTATION of the four inputs of a 1-D step — InsideLow/OutsideLow is the
-//     interior formula on (v2, v1, v0), InsideHigh/OutsideHigh on (v1, v2, v3), with the natural end slope
-//     k1 = 2 dy - k0 (multicubic/regular.rs:519-613) — and for dimensions whose four inputs come from four
-//     different loads (dimensions 0..N-3) or from four different lanes (dimension N-1) the permutation is applied to
-//     the load ADDRESS, which costs nothing per step. Only dimension N-2 (inside a sector) needs selects.
-// The 1-D steps are the reference's operation sequence with three exactly-equivalent fusions (cubic_step_perm).
+//     go through padded shared memory (two LDS.128 per point; conflict-free strides);
+//   * the saturation switch of the run-time steps is a PERMUTATION of the four inputs of a 1-D step — InsideLow /
+//     OutsideLow is the interior formula on (v2, v1, v0), InsideHigh / OutsideHigh on (v1, v2, v3), with the natural
+//     end slope k1 = 2 dy - k0 (multicubic/regular.rs:519-613). Every dimension's four inputs now come from four
+//     different loads (dimensions 1..N-2) or four different lanes (dimension N-1), so the permutation is applied to
+//     the load ADDRESS / lane index and costs nothing per step; dimension 0's class is the table slot.
+// The run-time 1-D steps are the reference's operation sequence with three exactly-equivalent fusions (cubic_step_perm).
 #pragma once
 #include "kernels.cuh"
 
-#ifndef IB200_QUAD4_UNROLLK
-#define IB200_QUAD4_UNROLLK 1
-#endif
-
 namespace ib200 {
-
-constexpr int kQuad4UnrollK = IB200_QUAD4_UNROLLK;  // outer row loop of a 4-D footprint (quad4_rows): 1 = rolled
 
 // Per-dimension parameters of a 1-D step.
 template <class T, bool RECT>
@@ -224,38 +230,79 @@ __device__ __forceinline__ T cubic_step_perm(T u0, T u1, T u2, T u3, const QuadD
     return out[0];
 }
 
-// Four steps on the rows of a sub-block (regular grids: four independent calls; the compiler interleaves them).
+// ---------------------------------------------------------------------------------------------
+// First-level coefficients (see the header). CubicCoef of a step on PERMUTED inputs: (y0, c1, c2, c3) of its Horner
+// polynomial y0 + tt*(c1 + tt*(c2 + tt*c3)), and (y1, k1) of the linearized extrapolation y1 + k1*(tt - 1) of an end
+// cell. Same operations in the same order as cubic_step_perm / cubic_step_tail up to the polynomial.
+// ---------------------------------------------------------------------------------------------
 template <class T>
-__device__ __forceinline__ void cubic_steps4(const T (&sub)[4][4], const QuadDim<T, false>& c, int fl, bool all_none, T (&out)[4]) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) out[j] = cubic_step_perm(sub[0][j], sub[1][j], sub[2][j], sub[3][j], c, fl, all_none);
-}
+struct CubicCoef {
+    T y0, c1, c2, c3, y1, k1;
+};
+
 template <class T>
-__device__ __forceinline__ void cubic_steps4(const T (&sub)[4][4], const QuadDim<T, true>& c, int fl, bool all_none, T (&out)[4]) {
-    cubic_steps_rect<4, T>(sub, c, fl, all_none, out);
+__device__ __forceinline__ CubicCoef<T> cubic_coef_perm(T u0, T u1, T u2, T u3, const QuadDim<T, false>&, int mode) {
+    using O = Ops<T>;
+    const T half = T(0.5), two = T(2);
+    CubicCoef<T> r;
+    const T dy = O::sub(u2, u1);
+    T a, b;
+    if (mode == kModeNone) {
+        const T d20 = O::sub(u2, u0);
+        a = O::fma(half, d20, -dy);
+        const T d31 = O::sub(u3, u1);
+        b = O::fma(-half, d31, dy);
+        r.k1 = O::mul(d31, half);  // interior cells are never extrapolated from: not stored
+    } else {
+        const T d20 = neg_zero_if(O::sub(u2, u0), mode == kModeLow);  // low end: the reference's -(v2 - v0)
+        a = O::fma(half, d20, -dy);
+        const T k0 = O::mul(d20, half);
+        r.k1 = O::fma(two, dy, -k0);
+        b = O::sub(dy, r.k1);
+    }
+    r.y0 = u1;
+    r.y1 = u2;
+    r.c1 = O::add(dy, a);
+    r.c2 = O::fma(-two, a, b);
+    r.c3 = O::sub(a, b);
+    return r;
 }
 
-// Two steps (the stashed outer rows of a 4-D footprint are reduced two in-sector positions at a time).
+// Rectilinear: the two quotients are plain IEEE divisions here (what exact_div returns by construction).
 template <class T>
-__device__ __forceinline__ void cubic_steps2(const T (&u)[4][2], const QuadDim<T, false>& c, int fl, bool all_none, T (&out)[2]) {
-#pragma unroll
-    for (int j = 0; j < 2; ++j) out[j] = cubic_step_perm(u[0][j], u[1][j], u[2][j], u[3][j], c, fl, all_none);
-}
-template <class T>
-__device__ __forceinline__ void cubic_steps2(const T (&u)[4][2], const QuadDim<T, true>& c, int fl, bool all_none, T (&out)[2]) {
-    cubic_steps_rect<2, T>(u, c, fl, all_none, out);
+__device__ __forceinline__ CubicCoef<T> cubic_coef_perm(T u0, T u1, T u2, T u3, const QuadDim<T, true>& c, int mode) {
+    using O = Ops<T>;
+    const T d10 = O::sub(u1, u0), dy = O::sub(u2, u1), d32 = O::sub(u3, u2);
+    const T q0 = O::div(d10, c.div0), q1 = O::div(d32, c.div1);
+    T k0 = cdn_sum(c.wa, dy, c.wc, q0);
+    T k1 = cdn_sum(c.wa1, q1, c.wc1, dy);
+    if (mode != kModeNone) {
+        if constexpr (kArithFma) k0 = mode == kModeLow ? cdn_sum(c.wc, q0, c.wa, dy) : k0;
+        k0 = neg_zero_if(k0, mode == kModeLow);  // low end: the reference negates the sum
+        k1 = O::fma(T(2), dy, -k0);
+    }
+    CubicCoef<T> r;
+    const T a = O::sub(k0, dy);  // hermite_fused
+    const T b = O::sub(dy, k1);
+    r.y0 = u1;
+    r.y1 = u2;
+    r.k1 = k1;
+    r.c1 = O::add(dy, a);
+    r.c2 = O::fma(T(-2), a, b);
+    r.c3 = O::sub(a, b);
+    return r;
 }
 
-// The same step on inputs in natural order: the permutation is done with selects (dimension N-2, whose four inputs
-// sit in one sector).
-template <class T, bool RECT>
-__device__ __forceinline__ T cubic_step_sel(T v0, T v1, T v2, T v3, const QuadDim<T, RECT>& c, int fl, bool all_none) {
-    if (all_none) return cubic_step_perm(v0, v1, v2, v3, c, fl, true);
-    const bool low = (fl & 3) == kModeLow, high = (fl & 3) == kModeHigh;
-    const T u0 = low ? v2 : (high ? v1 : v0);
-    const T u1 = high ? v2 : v1;
-    const T u2 = low ? v0 : (high ? v3 : v2);
-    return cubic_step_perm(u0, u1, u2, v3, c, fl, false);
+// A first-level step from its sector: the Horner polynomial, or — `lin`, the point lies outside the grid on dimension 0
+// and linearize_extrapolation is set — y1 + k1*(tt - 1) from the extrapolation slot (fused under the fma feature by the
+// regular-grid struct only: multicubic/regular.rs:553-564 against rectilinear.rs:480-540). `lin_any` is warp-uniform.
+template <bool RECT, class T>
+__device__ __forceinline__ T cubic_coef_eval(const T (&s)[4], T tt, bool lin, bool lin_any) {
+    using O = Ops<T>;
+    const T cub = muladd(muladd(muladd(s[3], tt, s[2]), tt, s[1]), tt, s[0]);
+    if (!lin_any) return cub;
+    const T linv = muladd<!RECT>(s[1], O::sub(tt, T(1)), s[0]);
+    return lin ? linv : cub;
 }
 
 // Row (or lane) order of the permuted inputs: interior 0,1,2,3; low end 2,1,0,3; high end 1,2,3,3.
@@ -327,8 +374,11 @@ __device__ __forceinline__ bool quad4_locate(const EvalArgs<T, N>& a, const T*, 
         const bool low = f <= 0, high = f >= dim - 2, outside = f < 0 || f > dim - 2;
         const int mode = low ? kModeLow : (high ? kModeHigh : kModeNone);
         s.tt[d] = low ? -t : (high ? O::sub(t, T(1)) : t);
-        base += origin * a.istride[d];
-        flags |= (mode | ((outside && a.linearize) ? 4 : 0)) << (4 * d);
+        const bool lin = outside && a.linearize;
+        // dimension 0 indexes the coefficient table by slot (header): 1 + cell, or the extrapolation slots 0 / dim
+        const int pos = d == 0 ? (lin ? (low ? 0 : dim) : min(max(f, 0), dim - 2) + 1) : origin;
+        base += pos * a.istride[d];
+        flags |= (mode | (lin ? 4 : 0)) << (4 * d);
     }
     s.base = base;
     s.flags = flags;
@@ -354,8 +404,12 @@ __device__ __forceinline__ bool quad4_locate(const EvalArgs<T, N>& a, const T* _
         const T e = O::sub(x[d], gref);
         s.tt[d] = exact_div((rf & 3) == kModeLow ? -e : e, href, rhref, (rf & 16) != 0);
         s.pp[d] = pp;
-        base += clamp_cell(pp - 2, a.dim[d] - 4) * a.istride[d];
-        flags |= ((rf & 3) | (((rf & 4) && a.linearize) ? 4 : 0) | (rf & 8)) << (4 * d);
+        const bool lin = (rf & 4) && a.linearize;
+        // dimension 0 indexes the coefficient table by slot (header): 1 + cell, or the extrapolation slots 0 / dim
+        const int pos = d == 0 ? (lin ? ((rf & 3) == kModeLow ? 0 : a.dim[d]) : clamp_cell(pp - 1, a.dim[d] - 2) + 1)
+                               : clamp_cell(pp - 2, a.dim[d] - 4);
+        base += pos * a.istride[d];
+        flags |= ((rf & 3) | (lin ? 4 : 0) | (rf & 8)) << (4 * d);
     }
     s.base = base;
     s.flags = flags;
@@ -367,103 +421,43 @@ __device__ __forceinline__ int cubic_perm_k(int mode, int k) {
     return mode == kModeLow ? (k < 3 ? 2 - k : 3) : (mode == kModeHigh ? min(k + 1, 3) : k);
 }
 
-// Reduces dimensions 0..D-1 (address dimensions, D <= N-2) of the sub-block at sector index `idx` for the four
-// in-sector positions at once; the rows of each dimension are visited in the permuted order of its saturation class.
-// The per-dimension parameters are read from the owner's slot (and the cell table) where they are used, so they are
-// live only for the steps of their dimension.
-// 16-byte vector of two T (f64: double2, f32: two pairs are wasted bandwidth-wise but keep one code path: float4 holds 4).
-template <class T> struct Stash2;
-template <> struct Stash2<double> { using V = double2; };
-template <> struct Stash2<float> { using V = float2; };
-
-#ifndef IB200_QUAD4_STASH
-#define IB200_QUAD4_STASH 1
+// Reduces dimensions 0..D-1 (D >= 1) of the sub-block whose first-level sector index is `idx`: dimension 0 from the
+// coefficient sectors, dimensions 1..D-1 by run-time steps whose four inputs are visited in the permuted order of the
+// dimension's saturation class. Per-dimension parameters are read from the owner's slot (and the cell table) where
+// they are used, so they are live only for the step of their dimension.
+#ifndef IB200_QUAD4_UNROLL_OUTER
+#define IB200_QUAD4_UNROLL_OUTER 1  // outermost loop of a 4-D footprint: 1 = rolled (four inner groups of 4 loads), 4 = unrolled
 #endif
-// N = 4: the partial results of the outer row loop (four rows of dimension 1 x four in-sector positions = 16 values per
-// lane) are parked in shared memory instead of registers. With them in registers the 4-D kernels needed 122-128
-// registers (2 CTAs per SM, 24 % of the warps: profiles/r1_p5_x4_ncu.json) and sat on load latency; per-thread columns
-// of `stash` ([8 vectors of two values][kBlock threads], consecutive threads in consecutive vectors: conflict-free).
-constexpr bool kQuad4Stash = IB200_QUAD4_STASH != 0;
-#ifndef IB200_QUAD4_INNER2
-#define IB200_QUAD4_INNER2 0
-#endif
-constexpr bool kQuad4Inner2 = IB200_QUAD4_INNER2 != 0;
-// Measured and dropped (round 2, gpurun_out/r2_exp3, commit "prefetch variant"): issuing the four sector loads of row
-// k+1 before the steps of row k from a second register block (software pipeline, 128 registers with ~150 bytes of
-// spills) ran 4-D regular 32^4 at 4.65 instead of 6.49 G points/s and 4-D rectilinear 32^4 at 1.51 instead of 2.37.
-
+constexpr int kQuad4UnrollOuter = IB200_QUAD4_UNROLL_OUTER;
 template <int D, class T, int N, bool RECT>
-__device__ __forceinline__ void quad4_rows(const EvalArgs<T, N>& a, const T* __restrict__ axes, int idx,
-                                           const QuadSlot<T, N, RECT>* sp, int flags, unsigned none_mask,
-                                           typename Stash2<T>::V* __restrict__ stash, T (&out)[4]) {
-    if constexpr (D == 0) {
-        load_row<T, 4, true, int>(nullptr, a.win, idx, out);
+__device__ __forceinline__ T quad4_reduce(const EvalArgs<T, N>& a, const T* __restrict__ axes, int idx,
+                                          const QuadSlot<T, N, RECT>* sp, T tt0, int flags, unsigned none_mask, bool lin_any) {
+    if constexpr (D == 1) {
+        T s[4];
+        load_row<T, 4, true, int>(nullptr, a.win, idx, s);
+        return cubic_coef_eval<RECT>(s, tt0, (flags & 4) != 0, lin_any);
     } else {
         const int fl = flags >> (4 * (D - 1));
         const bool all_none = (none_mask >> (D - 1)) & 1u;
         const int mode = all_none ? 0 : (fl & 3), stride = a.istride[D - 1];
-        if constexpr (D >= 2 && kQuad4Stash) {
-            using V = typename Stash2<T>::V;
-            // Not unrolled (code size: a 4-D footprint unrolled 16 ways did not fit the instruction cache).
-#pragma unroll(kQuad4UnrollK)
+        T u0, u1, u2, u3;
+        if constexpr (D >= 3) {
+            u0 = u1 = u2 = u3 = T(0);
+            // the four sub-results are shifted through u0..u3 so that no register array is indexed dynamically
+#pragma unroll(kQuad4UnrollOuter)
             for (int k = 0; k < 4; ++k) {
-                T rk[4];
-                quad4_rows<D - 1, T, N, RECT>(a, axes, idx + cubic_perm_k(mode, k) * stride, sp, flags, none_mask, stash, rk);
-                V lo, hi;
-                lo.x = rk[0]; lo.y = rk[1]; hi.x = rk[2]; hi.y = rk[3];
-                stash[(2 * k) * kBlock] = lo;
-                stash[(2 * k + 1) * kBlock] = hi;
-            }
-            const QuadDim<T, RECT> c = quad4_dim<T, N>(a, axes, sp, D - 1);
-            // two in-sector positions at a time: half the live inputs and temporaries of four interleaved steps
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                T u[4][2];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const V v = stash[(2 * k + h) * kBlock];
-                    u[k][0] = v.x; u[k][1] = v.y;
-                }
-                T o2[2];
-                if (all_none) cubic_steps2(u, c, fl, true, o2);
-                else cubic_steps2(u, c, fl, false, o2);
-                out[2 * h] = o2[0]; out[2 * h + 1] = o2[1];
+                const T v = quad4_reduce<D - 1, T, N, RECT>(a, axes, idx + cubic_perm_k(mode, k) * stride, sp, tt0, flags, none_mask, lin_any);
+                u0 = u1; u1 = u2; u2 = u3; u3 = v;
             }
         } else {
-            T sub[4][4];
-            if constexpr (D >= 2) {
-                // The four partial rows are shifted through `sub` so that no register array is indexed dynamically.
-#pragma unroll(kQuad4UnrollK)
-                for (int k = 0; k < 4; ++k) {
-                    T rk[4];
-                    quad4_rows<D - 1, T, N, RECT>(a, axes, idx + cubic_perm_k(mode, k) * stride, sp, flags, none_mask, stash, rk);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        sub[0][j] = sub[1][j]; sub[1][j] = sub[2][j]; sub[2][j] = sub[3][j]; sub[3][j] = rk[j];
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    quad4_rows<D - 1, T, N, RECT>(a, axes, idx + cubic_perm_k(mode, k) * stride, sp, flags, none_mask, stash, sub[k]);
-            }
-            const QuadDim<T, RECT> c = quad4_dim<T, N>(a, axes, sp, D - 1);
-            if constexpr (N >= 4 && kQuad4Inner2) {
-                // 4-D: two steps at a time (fewer live temporaries; the kernel is bound by registers, not by ILP)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    T u[4][2], o2[2];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) { u[k][0] = sub[k][2 * h]; u[k][1] = sub[k][2 * h + 1]; }
-                    if (all_none) cubic_steps2(u, c, fl, true, o2);
-                    else cubic_steps2(u, c, fl, false, o2);
-                    out[2 * h] = o2[0]; out[2 * h + 1] = o2[1];
-                }
-            } else {
-                if (all_none) cubic_steps4(sub, c, fl, true, out);  // one warp-uniform branch around the four independent steps
-                else cubic_steps4(sub, c, fl, false, out);
-            }
+            u0 = quad4_reduce<D - 1, T, N, RECT>(a, axes, idx + cubic_perm_k(mode, 0) * stride, sp, tt0, flags, none_mask, lin_any);
+            u1 = quad4_reduce<D - 1, T, N, RECT>(a, axes, idx + cubic_perm_k(mode, 1) * stride, sp, tt0, flags, none_mask, lin_any);
+            u2 = quad4_reduce<D - 1, T, N, RECT>(a, axes, idx + cubic_perm_k(mode, 2) * stride, sp, tt0, flags, none_mask, lin_any);
+            u3 = quad4_reduce<D - 1, T, N, RECT>(a, axes, idx + 3 * stride, sp, tt0, flags, none_mask, lin_any);
         }
+        const QuadDim<T, RECT> c = quad4_dim<T, N>(a, axes, sp, D - 1);
+        if (all_none) return cubic_step_perm(u0, u1, u2, u3, c, fl, true);  // one warp-uniform branch
+        return cubic_step_perm(u0, u1, u2, u3, c, fl, false);
     }
 }
 
@@ -472,14 +466,9 @@ __host__ __device__ constexpr int quad4_slot_warp_bytes() {  // one slot per lan
     return 32 * static_cast<int>(sizeof(QuadSlot<T, N, RECT>)) + 8 * 16;
 }
 constexpr int kQuad4XposeQuad = 20;  // transposition buffer [quad][lane j][point p]: quad stride 16 + 4 elements
-template <class T, int N>
-__host__ __device__ constexpr size_t quad4_stash_bytes() {  // eight 2-element vectors per thread, N = 4 only
-    return (N >= 4 && kQuad4Stash) ? static_cast<size_t>(kBlock) * 8 * 2 * sizeof(T) : 0;
-}
 template <class T, int N, bool RECT>
 __host__ __device__ constexpr size_t quad4_smem_bytes() {  // beyond the staged axes
-    return static_cast<size_t>(kBlock / 32) * (quad4_slot_warp_bytes<T, N, RECT>() + 8 * kQuad4XposeQuad * sizeof(T)) +
-           quad4_stash_bytes<T, N>();
+    return static_cast<size_t>(kBlock / 32) * (quad4_slot_warp_bytes<T, N, RECT>() + 8 * kQuad4XposeQuad * sizeof(T));
 }
 
 template <class T, int N, bool RECT, int MINB>
@@ -506,8 +495,6 @@ __global__ void __launch_bounds__(kBlock, MINB) cubic_quad4_kernel(const __grid_
     Slot* myslot = reinterpret_cast<Slot*>(wslots) + lane;
     const Slot* qslots = reinterpret_cast<const Slot*>(wslots) + (lane & ~3u);
     T* xq = s_xpose + (warp * 8 + quad) * kQuad4XposeQuad;
-    // per-thread column of the stash (16-byte aligned: every region before it is a multiple of 16 bytes)
-    typename Stash2<T>::V* stash = reinterpret_cast<typename Stash2<T>::V*>(s_xpose + kWarps * 8 * kQuad4XposeQuad) + threadIdx.x;
 
     // The coordinates of the NEXT block of points are requested after the last gather of the current one has been
     // consumed (its registers are free again), so their DRAM latency overlaps the transposition, the final step
@@ -521,30 +508,29 @@ __global__ void __launch_bounds__(kBlock, MINB) cubic_quad4_kernel(const __grid_
     for (int d = 0; d < N; ++d) x[d] = load_query(a.obs[d] + (valid ? i : a.n - 1));
     for (;;) {
         bool ok;
-        unsigned edges[N];  // lanes (= points) of the warp that are in an end cell of dimension d
+        unsigned edges[N];  // d >= 1: lanes (= points) of the warp in an end cell of dimension d; d = 0: linearized on dimension 0
         {
             Slot mine;
             ok = quad4_locate<T, N>(a, axes, x, mine);
             if (!ok) mine.base = 0;  // keep the gathers in range; the result is discarded
             *myslot = mine;
+            edges[0] = __ballot_sync(0xffffffffu, (mine.flags & 4) != 0);
 #pragma unroll
-            for (int d = 0; d < N; ++d) edges[d] = __ballot_sync(0xffffffffu, ((mine.flags >> (4 * d)) & 3) != 0);
+            for (int d = 1; d < N; ++d) edges[d] = __ballot_sync(0xffffffffu, ((mine.flags >> (4 * d)) & 3) != 0);
         }
         __syncwarp();
 
         // The four points of the quad, one after the other. Each lane's partial result goes straight into the
-        // transposition buffer [lane j][point p]; unrolled only where the body is small (IB200_QUAD4_UNROLL).
+        // transposition buffer [lane j][point p]; unrolled only where the body is small (IB200_QUAD4_UNROLL3).
 #pragma unroll(kUnrollP)
         for (int p = 0; p < 4; ++p) {
             const Slot* sp = qslots + p;
             const int flags = sp->flags;
             unsigned none_mask = 0;
 #pragma unroll
-            for (int d = 0; d < N; ++d) none_mask |= (edges[d] & (0x11111111u << p)) == 0u ? (1u << d) : 0u;
-            T r[4];
-            quad4_rows<N - 2, T, N, RECT>(a, axes, sp->base + static_cast<int>(b), sp, flags, none_mask, stash, r);
-            const QuadDim<T, RECT> c = quad4_dim<T, N>(a, axes, sp, N - 2);
-            xq[b * 4 + p] = cubic_step_sel<T, RECT>(r[0], r[1], r[2], r[3], c, flags >> (4 * (N - 2)), (none_mask >> (N - 2)) & 1u);
+            for (int d = 1; d < N; ++d) none_mask |= (edges[d] & (0x11111111u << p)) == 0u ? (1u << d) : 0u;
+            const bool lin_any = (edges[0] & (0x11111111u << p)) != 0u;
+            xq[b * 4 + p] = quad4_reduce<N - 1, T, N, RECT>(a, axes, sp->base + static_cast<int>(b), sp, sp->tt[0], flags, none_mask, lin_any);
         }
         const unsigned long long i_cur = i;
         const bool valid_cur = valid;
@@ -570,6 +556,40 @@ __global__ void __launch_bounds__(kBlock, MINB) cubic_quad4_kernel(const __grid_
             else report_bad(a, i_cur);
         }
         if (!more) break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Builder of the coefficient layout (launch_cubic_build.cu): one thread per sector.
+// ---------------------------------------------------------------------------------------------
+template <class T, bool RECT>
+__global__ void __launch_bounds__(kBlock) build_coef_window_kernel(const T* __restrict__ vals, T* __restrict__ cwin, int dim0,
+                                                                   unsigned long long s0, const T* __restrict__ table0) {
+    const unsigned long long total = static_cast<unsigned long long>(dim0 + 1) * s0;
+    const unsigned long long gstride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+    for (unsigned long long k = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; k < total; k += gstride) {
+        const int slot = static_cast<int>(k / s0);
+        const unsigned long long r = k - static_cast<unsigned long long>(slot) * s0;
+        const bool lin = slot == 0 || slot == dim0;
+        const int cell = slot == 0 ? 0 : (slot == dim0 ? dim0 - 2 : slot - 1);
+        const int mode = cell == 0 ? kModeLow : (cell == dim0 - 2 ? kModeHigh : kModeNone);
+        const int origin = min(max(cell, 1) - 1, dim0 - 4);
+        T u[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) u[j] = vals[static_cast<unsigned long long>(origin + cubic_perm_k(mode, j)) * s0 + r];
+        QuadDim<T, RECT> c{};
+        if constexpr (RECT) {
+            // row pp = cell + 1 of axis 0's cell table (the in-grid variant of an end cell; the constants are the same)
+            const T* row = table0 + static_cast<size_t>(cell + 1) * kCubicCellRow;
+            c.wa = row[0]; c.wc = row[1]; c.div0 = row[2]; c.rdiv0 = row[3];
+            c.wa1 = row[4]; c.wc1 = row[5]; c.div1 = row[6]; c.rdiv1 = row[7];
+        }
+        const CubicCoef<T> q = cubic_coef_perm(u[0], u[1], u[2], u[3], c, mode);
+        T* dst = cwin + k * 4;
+        dst[0] = lin ? q.y1 : q.y0;
+        dst[1] = lin ? q.k1 : q.c1;
+        dst[2] = lin ? T(0) : q.c2;
+        dst[3] = lin ? T(0) : q.c3;
     }
 }
 

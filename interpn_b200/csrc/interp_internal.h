@@ -31,7 +31,8 @@ struct DeviceGrid {
     // (linear) or 4 (cubic). Present only for mid-size grids (window_policy in capi.cu).
     void* win = nullptr;
     int win_width = 0;
-    int win_cross = 0;         // cubic, N = 2..4: the cross-window layout of kernels.cuh cubic_quad_point
+    int win_cross = 0;         // not plain rows: linear N >= 2 the 2x2 patch layout, cubic N = 2..4 the coefficient layout
+    size_t win_bytes = 0;      // bytes of `win` (the coefficient layout holds (dim0 + 1) slots per node of the other dimensions)
     void* axes = nullptr;           // device, all rectilinear axes packed back to back
     int axis_off[kMaxNd] = {};      // element offset of axis d inside `axes`
     int axes_core = 0;              // elements of the blob before the cell tables (kernels that do not read them stage only this)
@@ -77,6 +78,15 @@ cudaError_t launch_check_bounds(const T* x, size_t n, T lo, T hi, T atol, int* f
 
 // Fills g.win from g.vals (stream-ordered).
 cudaError_t launch_build_window(const DeviceGrid& g, cudaStream_t stream);
+// The cubic coefficient layout (cubic_quad4.cuh; launch_cubic_build.cu), called by launch_build_window.
+cudaError_t launch_build_coef_window(const DeviceGrid& g, cudaStream_t stream);
+// Elements of the window copy of `g` for window width `w` (0 when there is none).
+inline size_t window_elems(const DeviceGrid& g, int w) {
+    if (!w) return 0;
+    if (g.method == 1 && g.ndims >= 2 && w == 4)  // INTERPN_B200_CUBIC: coefficient layout
+        return static_cast<size_t>(g.dim[0] + 1) * static_cast<size_t>(g.stride[0]) * 4;
+    return g.nvals * static_cast<size_t>(w);
+}
 
 // True when the kernels must index `vals` with 64-bit arithmetic (ref: lib.rs:119-144 indexes with usize): grids of
 // 2^31 values or more, or any grid while INTERPN_B200_INDEX64=1 (test hook: runs the `long long` instantiations on

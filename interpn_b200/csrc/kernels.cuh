@@ -919,111 +919,6 @@ __device__ __forceinline__ bool cubic_point(const EvalArgs<T, N>& a, const T* __
     return true;
 }
 
-// ---------------------------------------------------------------------------------------------
-// Quad-cooperative multicubic, N = 2..4: four lanes per query point over the *cross-window layout*
-//   xwin[f*4 + b] = vals[f + min(b, D_{N-2} - 1 - i_{N-2}) * D_{N-1}],   f = flat C-order index,
-// i.e. the 32-byte sector at flat index f holds the four consecutive nodes of dimension N-2 that start at f,
-// and the sectors of consecutive last-dimension nodes are consecutive in memory. Lane j of a quad loads the
-// sector at f + j: one LDG.256 per lane fetches a point's 4x4 plane (dimensions N-2, N-1) as 128 contiguous
-// bytes (1 or 2 lines), so a 3-D footprint costs 4 x 1.75 = 7 L1 wavefronts instead of 16 (the L1 wavefront
-// rate of one line per clock per SM is what binds the one-thread-per-point kernel).
-// Work split: lane d locates dimension d and publishes the result by shuffles; every lane reduces
-// dimensions 0..N-3 (same code as cubic_rows) and then dimension N-2 on its own four values; dimension N-1
-// is evaluated on the four lanes' results gathered by shuffles. The 1-D steps and their order are the
-// reference's, so results are bit-identical.
-// ---------------------------------------------------------------------------------------------
-
-template <class T>
-__device__ __forceinline__ CubicRegDim<T> quad_bcast(const CubicRegDim<T>& c, int src) {
-    CubicRegDim<T> r;
-    r.tt = __shfl_sync(0xffffffffu, c.tt, src);
-    const int flags = __shfl_sync(0xffffffffu, c.mode | (c.lin ? 4 : 0), src);
-    r.mode = flags & 3;
-    r.lin = (flags & 4) != 0;
-    r.ttm1 = Ops<T>::sub(r.tt, T(1));
-    return r;
-}
-
-template <class T>
-__device__ __forceinline__ CubicRectDim<T> quad_bcast(const CubicRectDim<T>& c, int src) {
-    CubicRectDim<T> r;
-    r.tt = __shfl_sync(0xffffffffu, c.tt, src);
-    r.wa = __shfl_sync(0xffffffffu, c.wa, src);
-    r.wc = __shfl_sync(0xffffffffu, c.wc, src);
-    r.div0 = __shfl_sync(0xffffffffu, c.div0, src);
-    r.rdiv0 = __shfl_sync(0xffffffffu, c.rdiv0, src);
-    r.wa1 = __shfl_sync(0xffffffffu, c.wa1, src);
-    r.wc1 = __shfl_sync(0xffffffffu, c.wc1, src);
-    r.div1 = __shfl_sync(0xffffffffu, c.div1, src);
-    r.rdiv1 = __shfl_sync(0xffffffffu, c.rdiv1, src);
-    const int flags = __shfl_sync(0xffffffffu, c.mode | (c.lin ? 4 : 0) | (c.fast ? 8 : 0), src);
-    r.mode = flags & 3;
-    r.lin = (flags & 4) != 0;
-    r.fast = (flags & 8) != 0;
-    r.ttm1 = Ops<T>::sub(r.tt, T(1));
-    return r;
-}
-
-// One query point per quad. `x` is the point's coordinate along dimension min(b, N-1), b = lane & 3.
-// Must be called by all 32 lanes. Every lane of the quad returns the same `res` and status.
-template <class T, int N, bool RECT>
-__device__ __forceinline__ bool cubic_quad_point(const EvalArgs<T, N>& a, const T* __restrict__ axes, T x, T& res) {
-    static_assert(N >= 2 && N <= 4, "quad-cooperative cubic covers N = 2..4");
-    using Dim = typename CubicDimOf<T, RECT>::type;
-    const unsigned lane = threadIdx.x & 31u, b = lane & 3u, qbase = lane & ~3u;
-    const int dmine = b < static_cast<unsigned>(N) ? static_cast<int>(b) : N - 1;
-    Dim mine;
-    int origin;
-    bool ok = true;
-    if constexpr (RECT) {
-        cubic_rect_locate(x, axes + a.axis_off[dmine], rect_lower_bound<T, N>(a, axes, dmine, x), a.dim[dmine], a.linearize, origin, mine);
-    } else {
-        ok = cubic_regular_locate(x, a.start[dmine], a.step[dmine], a.rstep[dmine], a.fast_div != 0, a.dim[dmine],
-                                  a.linearize, origin, mine);
-    }
-    const unsigned bad = __ballot_sync(0xffffffffu, !ok);
-    const bool quad_ok = ((bad >> qbase) & 0xfu) == 0u;
-    Dim c[N];
-    long long base = b;  // this lane's sector: last-dimension node origin + b
-    unsigned none_mask = 0;
-#pragma unroll
-    for (int d = 0; d < N; ++d) {
-        c[d] = quad_bcast(mine, static_cast<int>(qbase) + d);
-        const int o = __shfl_sync(0xffffffffu, origin, static_cast<int>(qbase) + d);
-        base += static_cast<long long>(o) * a.stride[d];
-        none_mask |= __all_sync(0xffffffffu, c[d].mode == kModeNone) ? (1u << d) : 0u;
-    }
-    T r[4];
-    cubic_rows<N - 2, T, N, RECT, true>(nullptr, a.win, base, a.stride, c, none_mask, r);
-    const T s = cubic_step<T, RECT>(r[0], r[1], r[2], r[3], c[N - 2], (none_mask >> (N - 2)) & 1u);
-    const T w0 = __shfl_sync(0xffffffffu, s, static_cast<int>(qbase));
-    const T w1 = __shfl_sync(0xffffffffu, s, static_cast<int>(qbase) + 1);
-    const T w2 = __shfl_sync(0xffffffffu, s, static_cast<int>(qbase) + 2);
-    const T w3 = __shfl_sync(0xffffffffu, s, static_cast<int>(qbase) + 3);
-    res = cubic_step<T, RECT>(w0, w1, w2, w3, c[N - 1], (none_mask >> (N - 1)) & 1u);
-    return quad_ok;
-}
-
-template <class T, int N, bool RECT, int MINB>
-__global__ void __launch_bounds__(kBlock, MINB) cubic_quad_kernel(const __grid_constant__ EvalArgs<T, N> a) {
-    const T* axes = nullptr;
-    if constexpr (RECT) axes = stage_axes<T, N>(a);
-    const unsigned b = threadIdx.x & 3u;
-    const T* __restrict__ myobs = a.obs[b < static_cast<unsigned>(N) ? b : N - 1];
-    BlockSchedule sched;
-    while (sched.next(a.work, a.n * 4ull)) {  // four lanes per point: a block covers blockDim/4 consecutive points
-        const unsigned long long i = (sched.blk * blockDim.x + threadIdx.x) >> 2;
-        const bool valid = i < a.n;
-        const T x = load_query(myobs + (valid ? i : a.n - 1));
-        T res;
-        const bool ok = cubic_quad_point<T, N, RECT>(a, axes, x, res);
-        if (valid && b == 0u) {
-            if (ok) store_result(a.out + i, res);
-            else report_bad(a, i);
-        }
-    }
-}
-
 // MINB = CTAs per SM the register allocation must allow (launch_common.cuh cubic_min_blocks).
 template <class T, int N, bool RECT, bool WIN, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB) cubic_kernel(const __grid_constant__ EvalArgs<T, N> a) {

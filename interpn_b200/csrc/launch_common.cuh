@@ -174,19 +174,6 @@ constexpr int kMaxWindowDimsCubic = 4;
 #ifndef IB200_MINB_CUBIC4_RECT
 #define IB200_MINB_CUBIC4_RECT 3
 #endif
-// Quad-cooperative kernels (kernels.cuh cubic_quad_kernel): resident CTAs per SM the register budget must allow.
-#ifndef IB200_MINB_QUAD2
-#define IB200_MINB_QUAD2 3
-#endif
-#ifndef IB200_MINB_QUAD3
-#define IB200_MINB_QUAD3 4
-#endif
-#ifndef IB200_MINB_QUAD3_RECT
-#define IB200_MINB_QUAD3_RECT 2
-#endif
-#ifndef IB200_MINB_QUAD4
-#define IB200_MINB_QUAD4 2
-#endif
 template <int N, bool RECT>
 constexpr int cubic_min_blocks() {
     if (N == 3) return RECT ? IB200_MINB_CUBIC3_RECT : IB200_MINB_CUBIC3;

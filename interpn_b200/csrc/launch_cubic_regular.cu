@@ -10,7 +10,8 @@ template <class T>
 cudaError_t launch_cubic_regular(const DeviceGrid& g, const T* const* obs, size_t n, T* out,
                                  unsigned long long* first_bad, unsigned long long index_base, cudaStream_t stream) {
     cudaError_t err = cudaErrorInvalidValue;
-    // Window copies (capi.cu window_width): plain for N = 1, cross-window for N = 2..4 (quad-cooperative kernels).
+    // Window copies (capi.cu window_width): rows of four for N = 1, the coefficient layout for N = 2..4 (cubic_quad4.cuh;
+    // rectilinear: only when the axes have a cell table, i.e. are strictly increasing and finite).
     const bool has_win = g.win != nullptr && g.win_width == 4 && g.ndims <= kMaxWindowDimsCubic;
     // `remap` / `work` are set by the bin-swept path, which runs the same kernels on sorted coordinates.
     auto direct = [&](bool win, const T* const* o, size_t cnt, T* dst, unsigned long long base, const unsigned* remap,
@@ -27,40 +28,29 @@ cudaError_t launch_cubic_regular(const DeviceGrid& g, const T* const* obs, size_
         if (win && g.ndims == 1) {
             e = launch_generic<T, 1>(cubic_kernel<T, 1, false, true, 1>, g, o, cnt, dst, first_bad, base, stream, lo(1, true));
         } else if (win) {
-            // Four points per quad (cubic_quad4.cuh); INTERPN_B200_CUBIC_QUAD=1 selects the one-point-per-quad
-            // kernel of kernels.cuh, INTERPN_B200_QUAD4_MINB the register budget (CTAs per SM) for tuning runs.
-            static const int variant = static_cast<int>(sweep_env("INTERPN_B200_CUBIC_QUAD", 4));
+            // Four points per quad over the coefficient layout (cubic_quad4.cuh); INTERPN_B200_QUAD4_MINB selects the
+            // register budget (CTAs per SM) for tuning runs.
             static const int minb = static_cast<int>(sweep_env("INTERPN_B200_QUAD4_MINB", 0));
-            if (variant == 4) {
-                auto q4 = [&](auto kernel, auto ntag) {
-                    constexpr int N = decltype(ntag)::value;
-                    LaunchOpts r = lo(1, true);
-                    r.extra_smem = quad4_smem_bytes<T, N, false>();
-                    return launch_generic<T, N>(kernel, g, o, cnt, dst, first_bad, base, stream, r);
-                };
-                using std::integral_constant;
-                switch (g.ndims) {
-                    case 2: e = q4(cubic_quad4_kernel<T, 2, false, 4>, integral_constant<int, 2>()); break;
-                    case 3:
-                        if (minb == 3) e = q4(cubic_quad4_kernel<T, 3, false, 3>, integral_constant<int, 3>());
-                        else e = q4(cubic_quad4_kernel<T, 3, false, 4>, integral_constant<int, 3>());
-                        break;
-                    case 4:
-                        // 80 registers / 3 CTAs per SM now that the outer partial rows live in shared memory (cubic_quad4.cuh
-                        // stash): 6.68 against 6.49 (2 CTAs) and 5.00 (4 CTAs, spills) G points/s on 32^4, gpurun_out/r2_exp2
-                        if (minb == 2) e = q4(cubic_quad4_kernel<T, 4, false, 2>, integral_constant<int, 4>());
-                        else if (minb == 4) e = q4(cubic_quad4_kernel<T, 4, false, 4>, integral_constant<int, 4>());
-                        else e = q4(cubic_quad4_kernel<T, 4, false, 3>, integral_constant<int, 4>());
-                        break;
-                    default: break;
-                }
-            } else {
-                switch (g.ndims) {
-                    case 2: e = launch_generic<T, 2>(cubic_quad_kernel<T, 2, false, IB200_MINB_QUAD2>, g, o, cnt, dst, first_bad, base, stream, lo(4, true)); break;
-                    case 3: e = launch_generic<T, 3>(cubic_quad_kernel<T, 3, false, IB200_MINB_QUAD3>, g, o, cnt, dst, first_bad, base, stream, lo(4, true)); break;
-                    case 4: e = launch_generic<T, 4>(cubic_quad_kernel<T, 4, false, IB200_MINB_QUAD4>, g, o, cnt, dst, first_bad, base, stream, lo(4, true)); break;
-                    default: break;
-                }
+            auto q4 = [&](auto kernel, auto ntag) {
+                constexpr int N = decltype(ntag)::value;
+                LaunchOpts r = lo(1, true);
+                r.extra_smem = quad4_smem_bytes<T, N, false>();
+                return launch_generic<T, N>(kernel, g, o, cnt, dst, first_bad, base, stream, r);
+            };
+            using std::integral_constant;
+            switch (g.ndims) {
+                case 2: e = q4(cubic_quad4_kernel<T, 2, false, 4>, integral_constant<int, 2>()); break;
+                case 3:
+                    if (minb == 3) e = q4(cubic_quad4_kernel<T, 3, false, 3>, integral_constant<int, 3>());
+                    else if (minb == 5) e = q4(cubic_quad4_kernel<T, 3, false, 5>, integral_constant<int, 3>());
+                    else e = q4(cubic_quad4_kernel<T, 3, false, 4>, integral_constant<int, 3>());
+                    break;
+                case 4:
+                    if (minb == 2) e = q4(cubic_quad4_kernel<T, 4, false, 2>, integral_constant<int, 4>());
+                    else if (minb == 3) e = q4(cubic_quad4_kernel<T, 4, false, 3>, integral_constant<int, 4>());
+                    else e = q4(cubic_quad4_kernel<T, 4, false, 4>, integral_constant<int, 4>());
+                    break;
+                default: break;
             }
         } else {
             IB200_SWITCH_N(8, e = (launch_generic<T, N>(cubic_kernel<T, N, false, false, cubic_min_blocks<N, false>()>, g, o, cnt, dst, first_bad, base, stream, lo(1, false)));)
@@ -74,11 +64,11 @@ cudaError_t launch_cubic_regular(const DeviceGrid& g, const T* const* obs, size_
                         unsigned long long* work) {
             return direct(has_win, sobs, cnt, res, base, orig, work);
         };
-        IB200_SWITCH_N(kMaxWindowDimsCubic, if constexpr (N >= 2) err = (launch_sweep<T, N, false>(g, 4, has_win ? 4 : 1, 1 << (2 * (N - 1)), obs, n, out, first_bad, index_base, stream, eval, swept));)
+        IB200_SWITCH_N(kMaxWindowDimsCubic, if constexpr (N >= 2) err = (launch_sweep<T, N, false>(g, 4, has_win ? 4 : 1, 1 << (2 * (N - 1)), has_win ? 1 : 4, obs, n, out, first_bad, index_base, stream, eval, swept));)
         if (err != cudaSuccess || swept) return err;
     }
     // Direct kernels gather from the window layout only while it is L2-resident.
-    err = direct(has_win && g.nvals * sizeof(T) * 4 <= kWindowL2Bytes, obs, n, out, index_base, nullptr, nullptr);
+    err = direct(has_win && g.win_bytes <= kWindowL2Bytes, obs, n, out, index_base, nullptr, nullptr);
     return err;
 }
 

@@ -39,7 +39,7 @@ cudaError_t launch_linear_n(const DeviceGrid& g, const T* const* obs, size_t n, 
     if constexpr (N >= 2) {  // grids beyond L2: bin-swept evaluation (sweep.cuh), from the patch layout when there is one
         bool swept = false;
         cudaError_t e = launch_sweep<T, N, RECT>(
-            g, 2, has_patch ? kPatch : 1, has_patch ? 1 << (N - 2) : 1 << (N - 1), obs, n, out, first_bad, index_base, stream,
+            g, 2, has_patch ? kPatch : 1, has_patch ? 1 << (N - 2) : 1 << (N - 1), 2, obs, n, out, first_bad, index_base, stream,
             [&](const T* const* sobs, size_t cnt, T* res, const unsigned* orig, unsigned long long base, unsigned long long* work) {
                 if constexpr (kCanWin) {
                     if (has_patch) return launch_linear_direct<T, N, RECT, kPatch>(g, sobs, cnt, res, first_bad, base, stream, orig, work);

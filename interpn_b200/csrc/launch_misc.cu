@@ -33,23 +33,6 @@ __global__ void __launch_bounds__(kBlock) build_window_kernel(const T* __restric
     }
 }
 
-// Cross-window layout (kernels.cuh cubic_quad_point): xwin[f*4 + b] = vals[f + min(b, Da - 1 - i_a) * Db], where
-// a = N-2, b-dimension = N-1 and f is the flat C-order index.
-template <class T>
-__global__ void __launch_bounds__(kBlock) build_xwindow_kernel(const T* __restrict__ vals, T* __restrict__ xwin,
-                                                               unsigned long long nvals, unsigned long long da,
-                                                               unsigned long long db) {
-    const unsigned long long total = nvals * 4;
-    const unsigned long long gstride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
-    for (unsigned long long k = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; k < total;
-         k += gstride) {
-        const unsigned long long f = k >> 2, b = k & 3;
-        const unsigned long long ia = (f / db) % da;
-        const unsigned long long bb = ia + b < da ? b : da - 1 - ia;
-        xwin[k] = vals[f + bb * db];
-    }
-}
-
 // Patch layout (kernels.cuh linear_patches): pwin[f*4 + 2*i + j] = vals[f + i*Db + j], with i and j dropped to 0 where
 // the patch would leave the grid (never read: a footprint origin is at most dim-2).
 template <class T>
@@ -77,13 +60,7 @@ cudaError_t launch_build_window(const DeviceGrid& g, cudaStream_t stream) {
         count_launch();
         return cudaGetLastError();
     }
-    if (g.win_cross) {
-        const unsigned long long da = g.dim[g.ndims - 2], db = g.dim[g.ndims - 1];
-        if (g.elem == 8) build_xwindow_kernel<double><<<grid_dim, kBlock, 0, stream>>>(static_cast<const double*>(g.vals), static_cast<double*>(g.win), g.nvals, da, db);
-        else build_xwindow_kernel<float><<<grid_dim, kBlock, 0, stream>>>(static_cast<const float*>(g.vals), static_cast<float*>(g.win), g.nvals, da, db);
-        count_launch();
-        return cudaGetLastError();
-    }
+    if (g.win_cross) return launch_build_coef_window(g, stream);  // INTERPN_B200_CUBIC, N = 2..4
     if (g.elem == 8) {
         if (g.win_width == 4) build_window_kernel<double, 4><<<grid_dim, kBlock, 0, stream>>>(static_cast<const double*>(g.vals), static_cast<double*>(g.win), g.nvals);
         else build_window_kernel<double, 2><<<grid_dim, kBlock, 0, stream>>>(static_cast<const double*>(g.vals), static_cast<double*>(g.win), g.nvals);

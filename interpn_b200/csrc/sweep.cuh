@@ -318,9 +318,10 @@ size_t sweep_env(const char* name, size_t fallback);
 
 // Decide whether `n` points on grid `g` are worth sweeping and fill the key description. `fp` is the
 // footprint width (2 linear, 4 cubic); `row_bytes_scale` the blow-up of the array the kernel gathers
-// from (1 for vals, W for the window layout); `rows` the 32-byte sectors a point's footprint touches.
+// from (1 for vals, W for the window layout); `rows` the 32-byte sectors a point's footprint touches; `fp0` the
+// footprint along dimension 0 of the gathered array (1 for the cubic coefficient layout: one slot per cell).
 template <class T, int N>
-inline bool plan_sweep(const DeviceGrid& g, size_t n, int fp, int row_bytes_scale, int rows, bool axes_in_smem, SweepKey& s) {
+inline bool plan_sweep(const DeviceGrid& g, size_t n, int fp, int row_bytes_scale, int rows, int fp0, bool axes_in_smem, SweepKey& s) {
     const size_t gathered = g.nvals * sizeof(T) * static_cast<size_t>(row_bytes_scale);
     const size_t min_bytes = sweep_env("INTERPN_B200_SWEEP_MIN_MB", 96) << 20;
     const size_t min_points = sweep_env("INTERPN_B200_SWEEP_MIN_POINTS", size_t(1) << 21);
@@ -338,7 +339,8 @@ inline bool plan_sweep(const DeviceGrid& g, size_t n, int fp, int row_bytes_scal
     for (int d = 0; d < N - 1 && d < kSweepKeyDims; ++d) {
         if (slab <= target) break;
         const int cells = g.dim[d] - 1;  // sweep_cell() values 0 .. dim-2
-        int per = static_cast<int>(target * g.dim[d] / slab) - (fp - 1);
+        const int fpd = d == 0 ? fp0 : fp;
+        int per = static_cast<int>(target * g.dim[d] / slab) - (fpd - 1);
         per = per < 1 ? 1 : (per > cells ? cells : per);
         int groups = (cells + per - 1) / per;
         if (bins * groups > kSweepMaxBins) {
@@ -349,7 +351,7 @@ inline bool plan_sweep(const DeviceGrid& g, size_t n, int fp, int row_bytes_scal
         }
         s.rgrp[d] = 1.0f / static_cast<float>(per);
         s.ngrp[d] = groups;
-        slab = slab * (per + fp - 1) / g.dim[d];
+        slab = slab * (per + fpd - 1) / g.dim[d];
         bins *= groups;
         s.nkey = d + 1;
     }
@@ -367,14 +369,14 @@ inline bool plan_sweep(const DeviceGrid& g, size_t n, int fp, int row_bytes_scal
 // block scheduling (`work`, a zeroed device counter): blocks of points are handed out in key order on demand,
 // so the CTAs never drift apart along the key range.
 template <class T, int N, bool RECT, class Eval>
-inline cudaError_t launch_sweep(const DeviceGrid& g, int fp, int row_bytes_scale, int rows, const T* const* obs, size_t n,
+inline cudaError_t launch_sweep(const DeviceGrid& g, int fp, int row_bytes_scale, int rows, int fp0, const T* const* obs, size_t n,
                                 T* out, unsigned long long* first_bad, unsigned long long index_base, cudaStream_t stream,
                                 Eval&& eval, bool& used) {
     used = false;
     if (n == 0) return cudaSuccess;
     EvalArgs<T, N> a = make_args<T, N>(g, obs, n, out, first_bad, index_base);
     SweepKey key{};
-    if (!plan_sweep<T, N>(g, n, fp, row_bytes_scale, rows, a.axes_in_smem != 0, key)) return cudaSuccess;
+    if (!plan_sweep<T, N>(g, n, fp, row_bytes_scale, rows, fp0, a.axes_in_smem != 0, key)) return cudaSuccess;
     const size_t axes_bytes = a.axes_in_smem ? (static_cast<size_t>(g.axes_total) * sizeof(T) + 15) / 16 * 16 : 0;
     const size_t hist_smem = axes_bytes + static_cast<size_t>(key.nbins) * sizeof(unsigned);
     cudaError_t e;

@@ -268,7 +268,7 @@ int regular_new(int method, const size_t* dims, size_t ndims, const T* starts, s
 // in T, with the same IEEE operations in the same order as kernels.cuh cubic_rect_locate (this file is compiled with
 // -ffp-contract=off), so a kernel that reads them gets the bits it would have computed — without eight divisions per
 // dimension per query point. Only built for strictly increasing finite axes (no NaN/inf can arise).
-// Row layout (12 elements): wa, wc (exchanged in a low end cell, see cubic_quad4.cuh), div0, 1/div0, wa1, wc1, div1,
+// Row layout (12 elements, padded to cubic_cell_row_stride): wa, wc (exchanged in a low end cell, see cubic_quad4.cuh), div0, 1/div0, wa1, wc1, div1,
 // 1/div1, gref, href, 1/href (t = +-(x - gref)/href), flags (int bits: CubicMode | outside<<2 | ratios in exact_div's
 // range<<3 | href in range<<4).
 template <class T>
@@ -316,8 +316,8 @@ void cubic_cell_table(const T* g, size_t n, std::vector<T>& packed) {
         const int flags = mode | (outside << 2) | ((in_range(div0) && in_range(div1)) ? 8 : 0) | (in_range(href) ? 16 : 0);
         T fbits = T(0);
         memcpy(&fbits, &flags, sizeof(int));
-        const T row[12] = {wa, wc, div0, rdiv0, wa1, wc1, div1, rdiv1, gref, href, rhref, fbits};
-        packed.insert(packed.end(), row, row + 12);
+        const T row[14] = {wa, wc, div0, rdiv0, wa1, wc1, div1, rdiv1, gref, href, rhref, fbits, T(0), T(0)};
+        packed.insert(packed.end(), row, row + cubic_cell_row_stride(static_cast<int>(sizeof(T))));
     }
 }
 

@@ -32,6 +32,7 @@
 //     the load ADDRESS / lane index and costs nothing per step; dimension 0's class is the table slot.
 // The run-time 1-D steps are the reference's operation sequence with three exactly-equivalent fusions (cubic_step_perm).
 #pragma once
+#include "interp_internal.h"
 #include "kernels.cuh"
 
 namespace ib200 {
@@ -48,34 +49,67 @@ template <class T>
 struct QuadDim<T, true> {
     T tt, wa, wc, div0, rdiv0, wa1, wc1, div1, rdiv1;
 };
-constexpr int kCubicCellRow = 12;  // elements per table row (capi.cu cubic_cell_table)
+// Elements per row of the cell table (capi.cu cubic_cell_table; interp_internal.h cubic_cell_row_stride): 12 used, f64
+// rows padded to 14 so that the 16-byte chunks of eight random rows fall into eight different bank groups.
+template <class T>
+constexpr int kCubicCellRow = cubic_cell_row_stride(static_cast<int>(sizeof(T)));
 
 // What the owner of a point publishes to its quad. flags, four bits per dimension d: bits 4d..4d+1 = CubicMode,
 // bit 4d+2 = linearized extrapolation applies, bit 4d+3 = the spacing ratios are within exact_div's range (rectilinear).
 template <class T, int N, bool RECT>
-struct alignas(16) QuadSlot {
+struct QuadSlot {
     T tt[N];
-    int base;  // flat index of the footprint's first corner
-    int flags;
-};
-template <class T, int N>
-struct alignas(16) QuadSlot<T, N, true> {
-    T tt[N];
-    int pp[N];  // partition_point(g < x) per dimension = row of the cell table
-    int base;
+    int pp[RECT ? N : 1];  // rectilinear: partition_point(g < x) per dimension = row of the cell table
+    int base;              // sector index of the footprint's first corner in the coefficient layout
     int flags;
 };
 
+// Per-warp parameter block in shared memory, a structure of arrays so that both sides are conflict-free
+// (profiles/r2_c2_coef_ncu.json: with one 32-byte struct per lane the owner's 64-bit accesses took 4 wavefronts instead
+// of 2): the owner of point e (= its lane) accesses element e of every array — consecutive lanes, consecutive words —
+// and the four lanes of a quad read element 4q + p. Arrays of 64-bit elements leave one pad element between the two
+// half-warps (a 64-bit access is served per half-warp; without it quads q and q+4 meet in the same banks).
+template <class T, int N, bool RECT>
+struct QuadParams {
+    static constexpr int kTStride = 34;                 // elements per T array: 32 + the pad (+1: keeps 16-byte multiples)
+    static constexpr int kInts = 2 + (RECT ? N : 0);    // base, flags, pp[N]
+    static constexpr int kBytes = (N * kTStride * static_cast<int>(sizeof(T)) + kInts * 32 * 4 + 15) / 16 * 16;
+    unsigned char* w;
+    __device__ __forceinline__ T* tt(int d) const { return reinterpret_cast<T*>(w) + d * kTStride; }
+    __device__ __forceinline__ int* ints(int k) const { return reinterpret_cast<int*>(w + N * kTStride * sizeof(T)) + k * 32; }
+    static __device__ __forceinline__ int pad(int e) { return sizeof(T) == 8 ? e + (e >> 4) : e; }
+    __device__ __forceinline__ void publish(int e, const QuadSlot<T, N, RECT>& m) const {
+#pragma unroll
+        for (int d = 0; d < N; ++d) tt(d)[pad(e)] = m.tt[d];
+        ints(0)[e] = m.base;
+        ints(1)[e] = m.flags;
+        if constexpr (RECT) {
+#pragma unroll
+            for (int d = 0; d < N; ++d) ints(2 + d)[e] = m.pp[d];
+        }
+    }
+};
+// One point's parameters as seen by a reader.
+template <class T, int N, bool RECT>
+struct QuadRef {
+    QuadParams<T, N, RECT> P;
+    int e;
+    __device__ __forceinline__ T tt(int d) const { return P.tt(d)[P.pad(e)]; }
+    __device__ __forceinline__ int base() const { return P.ints(0)[e]; }
+    __device__ __forceinline__ int flags() const { return P.ints(1)[e]; }
+    __device__ __forceinline__ int pp(int d) const { return P.ints(2 + d)[e]; }
+};
+
 template <class T, int N>
-__device__ __forceinline__ QuadDim<T, false> quad4_dim(const EvalArgs<T, N>&, const T*, const QuadSlot<T, N, false>* sp, int d) {
-    return QuadDim<T, false>{sp->tt[d]};
+__device__ __forceinline__ QuadDim<T, false> quad4_dim(const EvalArgs<T, N>&, const T*, const QuadRef<T, N, false>& r, int d) {
+    return QuadDim<T, false>{r.tt(d)};
 }
 template <class T, int N>
 __device__ __forceinline__ QuadDim<T, true> quad4_dim(const EvalArgs<T, N>& a, const T* __restrict__ axes,
-                                                      const QuadSlot<T, N, true>* sp, int d) {
-    const T* row = axes + a.ct_off[d] + sp->pp[d] * kCubicCellRow;
+                                                      const QuadRef<T, N, true>& r, int d) {
+    const T* row = axes + a.ct_off[d] + r.pp(d) * kCubicCellRow<T>;
     QuadDim<T, true> c;
-    c.tt = sp->tt[d];
+    c.tt = r.tt(d);
     if constexpr (sizeof(T) == 8) {
         const double2 r0 = reinterpret_cast<const double2*>(row)[0], r1 = reinterpret_cast<const double2*>(row)[1];
         const double2 r2 = reinterpret_cast<const double2*>(row)[2], r3 = reinterpret_cast<const double2*>(row)[3];
@@ -396,11 +430,18 @@ __device__ __forceinline__ bool quad4_locate(const EvalArgs<T, N>& a, const T* _
 #pragma unroll
     for (int d = 0; d < N; ++d) {
         const int pp = rect_lower_bound<T, N>(a, axes, d, x[d]);
-        const T* row = axes + a.ct_off[d] + pp * kCubicCellRow;
-        const T gref = row[8], href = row[9], rhref = row[10];
+        const T* row = axes + a.ct_off[d] + pp * kCubicCellRow<T>;
+        T gref, href, rhref;
         int rf;
-        if constexpr (sizeof(T) == 8) rf = __double2loint(row[11]);
-        else rf = __float_as_int(row[11]);
+        if constexpr (sizeof(T) == 8) {  // two 16-byte loads (four 8-byte loads of 32 random rows cost 11 wavefronts each)
+            const double2 g = reinterpret_cast<const double2*>(row)[4], h = reinterpret_cast<const double2*>(row)[5];
+            gref = g.x; href = g.y; rhref = h.x;
+            rf = __double2loint(h.y);
+        } else {
+            const float4 g = reinterpret_cast<const float4*>(row)[2];
+            gref = g.x; href = g.y; rhref = g.z;
+            rf = __float_as_int(g.w);
+        }
         const T e = O::sub(x[d], gref);
         s.tt[d] = exact_div((rf & 3) == kModeLow ? -e : e, href, rhref, (rf & 16) != 0);
         s.pp[d] = pp;
@@ -431,7 +472,7 @@ __device__ __forceinline__ int cubic_perm_k(int mode, int k) {
 constexpr int kQuad4UnrollOuter = IB200_QUAD4_UNROLL_OUTER;
 template <int D, class T, int N, bool RECT>
 __device__ __forceinline__ T quad4_reduce(const EvalArgs<T, N>& a, const T* __restrict__ axes, int idx,
-                                          const QuadSlot<T, N, RECT>* sp, T tt0, int flags, unsigned none_mask, bool lin_any) {
+                                          const QuadRef<T, N, RECT>& sp, T tt0, int flags, unsigned none_mask, bool lin_any) {
     if constexpr (D == 1) {
         T s[4];
         load_row<T, 4, true, int>(nullptr, a.win, idx, s);
@@ -461,39 +502,46 @@ __device__ __forceinline__ T quad4_reduce(const EvalArgs<T, N>& a, const T* __re
     }
 }
 
-template <class T, int N, bool RECT>
-__host__ __device__ constexpr int quad4_slot_warp_bytes() {  // one slot per lane + 16 bytes of padding per quad (bank spreading)
-    return 32 * static_cast<int>(sizeof(QuadSlot<T, N, RECT>)) + 8 * 16;
-}
-constexpr int kQuad4XposeQuad = 20;  // transposition buffer [quad][lane j][point p]: quad stride 16 + 4 elements
+constexpr int kQuad4XposeQuad = 20;  // transposition buffer: element (node j, point p) of quad q at q*20 + 5j + p, see the kernel
 template <class T, int N, bool RECT>
 __host__ __device__ constexpr size_t quad4_smem_bytes() {  // beyond the staged axes
-    return static_cast<size_t>(kBlock / 32) * (quad4_slot_warp_bytes<T, N, RECT>() + 8 * kQuad4XposeQuad * sizeof(T));
+    return static_cast<size_t>(kBlock / 32) * (QuadParams<T, N, RECT>::kBytes + 8 * kQuad4XposeQuad * sizeof(T));
 }
 
-template <class T, int N, bool RECT, int MINB>
+// AXSM: the rectilinear axes blob (axes, bucket tables, cell tables) is staged in shared memory — the loads of the
+// tables are then LDS, not generic loads — else it is read from global memory through L1 (blobs beyond the budget).
+template <class T, int N, bool RECT, int MINB, bool AXSM = true>
 __global__ void __launch_bounds__(kBlock, MINB) cubic_quad4_kernel(const __grid_constant__ EvalArgs<T, N> a) {
     static_assert(N >= 2 && N <= 4, "quad-cooperative cubic covers N = 2..4");
-    using Slot = QuadSlot<T, N, RECT>;
+    using Params = QuadParams<T, N, RECT>;
     constexpr int kWarps = kBlock / 32;
 #ifndef IB200_QUAD4_UNROLL3
 #define IB200_QUAD4_UNROLL3 4
 #endif
     constexpr int kUnrollP = (!RECT && N <= 3) ? IB200_QUAD4_UNROLL3 : 1;
-    constexpr int kSlotWarpBytes = quad4_slot_warp_bytes<T, N, RECT>();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const T* axes = nullptr;
     size_t axes_bytes = 0;
     if constexpr (RECT) {
-        axes = stage_axes<T, N>(a);
-        if (a.axes_in_smem) axes_bytes = (static_cast<size_t>(a.axes_total) * sizeof(T) + 15) / 16 * 16;
+        if constexpr (AXSM) {
+            T* s_axes = reinterpret_cast<T*>(smem_raw);
+            for (int k = threadIdx.x; k < a.axes_total; k += blockDim.x) s_axes[k] = a.axes[k];
+            __syncthreads();
+            axes = s_axes;
+            axes_bytes = (static_cast<size_t>(a.axes_total) * sizeof(T) + 15) / 16 * 16;
+        } else {
+            axes = a.axes;
+        }
     }
-    unsigned char* s_slots = smem_raw + axes_bytes;
-    T* s_xpose = reinterpret_cast<T*>(s_slots + kWarps * kSlotWarpBytes);
+    unsigned char* s_params = smem_raw + axes_bytes;
+    T* s_xpose = reinterpret_cast<T*>(s_params + kWarps * Params::kBytes);
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, b = lane & 3u, quad = lane >> 2;
-    unsigned char* wslots = s_slots + warp * kSlotWarpBytes + quad * 16;
-    Slot* myslot = reinterpret_cast<Slot*>(wslots) + lane;
-    const Slot* qslots = reinterpret_cast<const Slot*>(wslots) + (lane & ~3u);
+    const Params params{s_params + warp * Params::kBytes};
+    const QuadRef<T, N, RECT> mine_ref{params, static_cast<int>(lane)};
+    // Transposition buffer of the quad: element (last-dimension node j, point p) at 5j + p, quads 20 elements apart. With
+    // this skew both sides are conflict-free for 64-bit elements: the writers of one point (lanes j, fixed p) fall on
+    // bank pairs 4q + 5j, the readers of one node (lanes p, fixed j) on 4q + p — all distinct within a half-warp (the
+    // former 4j + p layout made every write an 8-way conflict, 43 % of the kernel's shared-memory wavefronts).
     T* xq = s_xpose + (warp * 8 + quad) * kQuad4XposeQuad;
 
     // The coordinates of the NEXT block of points are requested after the last gather of the current one has been
@@ -510,10 +558,10 @@ __global__ void __launch_bounds__(kBlock, MINB) cubic_quad4_kernel(const __grid_
         bool ok;
         unsigned edges[N];  // d >= 1: lanes (= points) of the warp in an end cell of dimension d; d = 0: linearized on dimension 0
         {
-            Slot mine;
+            QuadSlot<T, N, RECT> mine;
             ok = quad4_locate<T, N>(a, axes, x, mine);
             if (!ok) mine.base = 0;  // keep the gathers in range; the result is discarded
-            *myslot = mine;
+            params.publish(static_cast<int>(lane), mine);
             edges[0] = __ballot_sync(0xffffffffu, (mine.flags & 4) != 0);
 #pragma unroll
             for (int d = 1; d < N; ++d) edges[d] = __ballot_sync(0xffffffffu, ((mine.flags >> (4 * d)) & 3) != 0);
@@ -521,16 +569,16 @@ __global__ void __launch_bounds__(kBlock, MINB) cubic_quad4_kernel(const __grid_
         __syncwarp();
 
         // The four points of the quad, one after the other. Each lane's partial result goes straight into the
-        // transposition buffer [lane j][point p]; unrolled only where the body is small (IB200_QUAD4_UNROLL3).
+        // transposition buffer; unrolled only where the body is small (IB200_QUAD4_UNROLL3).
 #pragma unroll(kUnrollP)
         for (int p = 0; p < 4; ++p) {
-            const Slot* sp = qslots + p;
-            const int flags = sp->flags;
+            const QuadRef<T, N, RECT> sp{params, static_cast<int>(lane & ~3u) + p};
+            const int flags = sp.flags();
             unsigned none_mask = 0;
 #pragma unroll
             for (int d = 1; d < N; ++d) none_mask |= (edges[d] & (0x11111111u << p)) == 0u ? (1u << d) : 0u;
             const bool lin_any = (edges[0] & (0x11111111u << p)) != 0u;
-            xq[b * 4 + p] = quad4_reduce<N - 1, T, N, RECT>(a, axes, sp->base + static_cast<int>(b), sp, sp->tt[0], flags, none_mask, lin_any);
+            xq[b * 5 + p] = quad4_reduce<N - 1, T, N, RECT>(a, axes, sp.base() + static_cast<int>(b), sp, sp.tt(0), flags, none_mask, lin_any);
         }
         const unsigned long long i_cur = i;
         const bool valid_cur = valid;
@@ -544,11 +592,11 @@ __global__ void __launch_bounds__(kBlock, MINB) cubic_quad4_kernel(const __grid_
         // Transposition: lane j holds the partial results of its last-dimension node for points 0..3; the owner of
         // point b needs the four nodes' results of point b, in the permuted order of its saturation class.
         __syncwarp();
-        const int fl = myslot->flags >> (4 * (N - 1));  // re-read from the slot: not kept live across the point loop
+        const int fl = mine_ref.flags() >> (4 * (N - 1));  // re-read: not kept live across the point loop
         int k4[4];
         cubic_perm(fl & 3, k4);
-        const T w0 = xq[k4[0] * 4 + b], w1 = xq[k4[1] * 4 + b], w2 = xq[k4[2] * 4 + b], w3 = xq[12 + b];
-        const QuadDim<T, RECT> c = quad4_dim<T, N>(a, axes, myslot, N - 1);
+        const T w0 = xq[k4[0] * 5 + b], w1 = xq[k4[1] * 5 + b], w2 = xq[k4[2] * 5 + b], w3 = xq[15 + b];
+        const QuadDim<T, RECT> c = quad4_dim<T, N>(a, axes, mine_ref, N - 1);
         const T res = cubic_step_perm(w0, w1, w2, w3, c, fl, edges[N - 1] == 0u);
         __syncwarp();  // the next iteration overwrites both buffers
         if (valid_cur) {
@@ -580,7 +628,7 @@ __global__ void __launch_bounds__(kBlock) build_coef_window_kernel(const T* __re
         QuadDim<T, RECT> c{};
         if constexpr (RECT) {
             // row pp = cell + 1 of axis 0's cell table (the in-grid variant of an end cell; the constants are the same)
-            const T* row = table0 + static_cast<size_t>(cell + 1) * kCubicCellRow;
+            const T* row = table0 + static_cast<size_t>(cell + 1) * kCubicCellRow<T>;
             c.wa = row[0]; c.wc = row[1]; c.div0 = row[2]; c.rdiv0 = row[3];
             c.wa1 = row[4]; c.wc1 = row[5]; c.div1 = row[6]; c.rdiv1 = row[7];
         }

@@ -14,6 +14,10 @@ namespace ib200 {
 
 constexpr int kMaxNd = 8;
 
+// Elements per row of the rectilinear cubic cell table (capi.cu cubic_cell_table, cubic_quad4.cuh): 12 used; f64 rows
+// are padded to 14 (112 bytes) so that the 16-byte chunks of random rows spread over all shared-memory bank groups.
+constexpr int cubic_cell_row_stride(int elem_bytes) { return elem_bytes == 8 ? 14 : 12; }
+
 // Grid resident in HBM. Host struct; pointers are device pointers.
 struct DeviceGrid {
     int method = 0;     // INTERPN_B200_LINEAR / CUBIC / NEAREST
@@ -48,7 +52,7 @@ struct DeviceGrid {
     int clut_nb[kMaxNd] = {};
     double clut_scale[kMaxNd] = {}; // buckets per unit length
     int rect_cubic_table = 0;       // cubic, strictly increasing finite axes: per-cell constant table present
-    int ct_off[kMaxNd] = {};        // element offset of axis d's cubic cell table (dim+1 rows of 12 elements, 16-byte aligned)
+    int ct_off[kMaxNd] = {};        // element offset of axis d's cubic cell table (dim+1 rows of cubic_cell_row_stride elements, 16-byte aligned)
     int sm_count = 148;
     unsigned long long grid_hash = 0;  // FNV-1a of dims and starts/steps or axes: two interpolators over the same grid agree
 };

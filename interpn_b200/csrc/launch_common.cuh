@@ -11,6 +11,13 @@ constexpr int kAxesSmemBudget = 96 * 1024;
 
 size_t sweep_env_common(const char* name, size_t fallback);
 
+// True when the kernels stage the rectilinear axes blob in shared memory (INTERPN_B200_AXES_SMEM_KB overrides the budget).
+template <class T>
+inline bool axes_fit_smem(const DeviceGrid& g) {
+    static const size_t axes_budget = sweep_env_common("INTERPN_B200_AXES_SMEM_KB", kAxesSmemBudget >> 10) << 10;
+    return g.rect && static_cast<size_t>(g.axes_total) * sizeof(T) <= axes_budget;
+}
+
 template <class T, int N>
 inline EvalArgs<T, N> make_args(const DeviceGrid& g, const T* const* obs, size_t n, T* out,
                                 unsigned long long* first_bad, unsigned long long index_base,
@@ -63,8 +70,7 @@ inline EvalArgs<T, N> make_args(const DeviceGrid& g, const T* const* obs, size_t
     a.rect_fast_div = g.rect_fast_div;
     a.rect_cubic_table = g.rect_cubic_table;
     a.rect_cell = g.rect_cell;
-    static const size_t axes_budget = sweep_env_common("INTERPN_B200_AXES_SMEM_KB", kAxesSmemBudget >> 10) << 10;
-    a.axes_in_smem = g.rect && static_cast<size_t>(g.axes_total) * sizeof(T) <= axes_budget;
+    a.axes_in_smem = axes_fit_smem<T>(g);
     a.linearize = g.linearize;
     a.first_bad = first_bad;
     a.index_base = index_base;

@@ -38,20 +38,25 @@ cudaError_t launch_cubic_rect(const DeviceGrid& g, const T* const* obs, size_t n
                 return launch_generic<T, N>(kernel, g, o, cnt, dst, first_bad, base, stream, r);
             };
             using std::integral_constant;
+            const bool in_smem = axes_fit_smem<T>(g);  // the blob staged in shared memory (LDS) or read through L1
+#define IB200_Q4R(NN, MB)                                                                                        \
+    e = in_smem ? q4(cubic_quad4_kernel<T, NN, true, MB, true>, integral_constant<int, NN>())                    \
+                : q4(cubic_quad4_kernel<T, NN, true, MB, false>, integral_constant<int, NN>())
             switch (g.ndims) {
-                case 2: e = q4(cubic_quad4_kernel<T, 2, true, 3>, integral_constant<int, 2>()); break;
+                case 2: IB200_Q4R(2, 3); break;
                 case 3:
-                    if (minb == 2) e = q4(cubic_quad4_kernel<T, 3, true, 2>, integral_constant<int, 3>());
-                    else if (minb == 4) e = q4(cubic_quad4_kernel<T, 3, true, 4>, integral_constant<int, 3>());
-                    else e = q4(cubic_quad4_kernel<T, 3, true, 3>, integral_constant<int, 3>());
+                    if (minb == 2) IB200_Q4R(3, 2);
+                    else if (minb == 4) IB200_Q4R(3, 4);
+                    else IB200_Q4R(3, 3);
                     break;
                 case 4:
-                    if (minb == 2) e = q4(cubic_quad4_kernel<T, 4, true, 2>, integral_constant<int, 4>());
-                    else if (minb == 4) e = q4(cubic_quad4_kernel<T, 4, true, 4>, integral_constant<int, 4>());
-                    else e = q4(cubic_quad4_kernel<T, 4, true, 3>, integral_constant<int, 4>());
+                    if (minb == 2) IB200_Q4R(4, 2);
+                    else if (minb == 4) IB200_Q4R(4, 4);
+                    else IB200_Q4R(4, 3);
                     break;
                 default: break;
             }
+#undef IB200_Q4R
         } else {
             IB200_SWITCH_N(8, e = (launch_generic<T, N>(cubic_kernel<T, N, true, false, cubic_min_blocks<N, true>()>, g, o, cnt, dst, first_bad, base, stream, lo(1, false)));)
         }

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 experiment 4: coefficient-layout cubic kernels — parity tests, then bench lines per register budget
-out=gpurun_out/r2_exp4; mkdir -p $out
+out=gpurun_out/${TAG:-r2_exp4}; mkdir -p $out
 ( time timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_instantiations.py tests/test_ref_docs_golden.py tests/test_gpu_reference_suite.py -m gpu -x -q -k "cubic or Cubic or docs or suite or baseline or plateau or sweep or swept" ) > $out/pytest_cubic.log 2>&1; tail -n 6 $out/pytest_cubic.log
 line() { # label env... -- bench args
   label=$1; shift; envs=(); while [ "$1" != "--" ]; do envs+=("$1"); shift; done; shift

@@ -110,6 +110,28 @@ __global__ void row_gather_kernel(const double* __restrict__ tab, unsigned nrows
     if (s == 123.456) out[0] = s;
 }
 
+// Quad-contiguous gathers (cubic_quad4.cuh): the four lanes of a quad load four consecutive 32-byte sectors (LDG.256
+// each) starting at a random sector (ALIGNED = 0: any sector, the 128 bytes straddle two lines 75 % of the time;
+// 1: a multiple of four sectors = one line). Counts sectors: the L2 -> L1 rate the coefficient layout can reach.
+template <int ALIGNED>
+__global__ void quad_gather_kernel(const double* __restrict__ tab, unsigned nsectors, int per, double* out) {
+    unsigned x = ((blockIdx.x * blockDim.x + threadIdx.x) >> 2) * 2654435761u + 12345u;  // quad-uniform stream
+    const unsigned j = threadIdx.x & 3u;
+    double s = 0;
+    for (int i = 0; i < per; i += 8) {
+        D4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            unsigned r = __umulhi(lcg(x), nsectors - 4);
+            if (ALIGNED) r &= ~3u;
+            v[k] = reinterpret_cast<const D4*>(tab)[r + j];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+    if (s == 123.456) out[0] = s;
+}
+
 // Random shared-memory gathers with cheap indices. W = 1: LDS.64, 2: LDS.128 (16-byte aligned pair).
 template <int W>
 __global__ void smem_gather2_kernel(const double* __restrict__ tab, int n, int per, double* out) {
@@ -234,6 +256,9 @@ int main() {
         printf(", \"row32B_ldg256_L2_Grows_s\": %.2f, \"row4x_ldg64_L2_Grows_s\": %.2f, \"row2x_ldg128_L2_Grows_s\": %.2f"
                ", \"pair_ldg128_L2_Gloads_s\": %.2f, \"ldg64_L2_Gloads_s\": %.2f, \"ldg64_L1hit_Gloads_s\": %.2f, \"ldg256_L1hit_Grows_s\": %.2f",
                rows / t0 * 1e-6, rows / t1 * 1e-6, rows / t2 * 1e-6, rows / t3 * 1e-6, rows / t4 * 1e-6, rows / t5 * 1e-6, rows / t6 * 1e-6);
+        float q0 = time_ms([&] { quad_gather_kernel<0><<<blocks, threads>>>(tab, n32 / 4, per, out); });
+        float q1 = time_ms([&] { quad_gather_kernel<1><<<blocks, threads>>>(tab, n32 / 4, per, out); });
+        printf(", \"quad128B_ldg256_L2_Gsectors_s\": %.2f, \"quad128B_aligned_ldg256_L2_Gsectors_s\": %.2f", rows / q0 * 1e-6, rows / q1 * 1e-6);
         CK(cudaFree(tab));
     }
     // ---- shared-memory gathers, cheap indices (96 KB tile, 2 CTAs per SM)

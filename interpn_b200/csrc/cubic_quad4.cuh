@@ -209,9 +209,11 @@ __device__ __forceinline__ T cubic_step_tail(T u1, T u2, T dy, T q0, T q1, const
     return (fl & 4) ? linv : cub;
 }
 
-// |v| in [2^-300, 2^301): exact_div's operand range, tested on the high word (three integer instructions).
+// |v| in [2^-300, 2^301) — exact_div's operand range, tested on the high word — or a zero, whose quotient by a positive
+// divisor is the zero itself (every term of the sequence is a zero; the caller's copysign restores -0).
 __device__ __forceinline__ bool exact_div_operand_ok(double v) {
-    return (static_cast<unsigned>(__double2hiint(v)) & 0x7fffffffu) - (723u << 20) < (601u << 20);
+    const unsigned h = static_cast<unsigned>(__double2hiint(v)) & 0x7fffffffu;
+    return (h - (723u << 20) < (601u << 20)) || (h | static_cast<unsigned>(__double2loint(v))) == 0u;
 }
 
 // M independent 1-D steps of one dimension (same parameters, inputs u[k][j]). f64: all 2M quotients take the
@@ -232,11 +234,16 @@ __device__ __forceinline__ void cubic_steps_rect(const T (&u)[4][M], const QuadD
     }
     if constexpr (sizeof(T) == 8) {
         bool ok = (fl & 8) != 0;
+        // q1 feeds the interior slope only: in an end cell its numerator is u3 - u2 with u3 a stand-in (permuted order
+        // 1,2,3,3 makes it exactly zero at the high end), so it must not send the lane to the IEEE division — that was
+        // 17 out-of-line divisions per 32 points on a batch with 10 % of the points outside the grid
+        // (profiles/r2_x4rect_coef_ncu.json). The spacing ratios are positive, so copysign only matters for a zero numerator.
+        const bool end = !all_none && (fl & 3) != 0;
 #pragma unroll
         for (int j = 0; j < M; ++j) {
-            q0[j] = markstein_div_raw(d10[j], c.div0, c.rdiv0);
-            q1[j] = markstein_div_raw(d32[j], c.div1, c.rdiv1);
-            ok = ok && exact_div_operand_ok(d10[j]) && exact_div_operand_ok(d32[j]);
+            q0[j] = copysign(markstein_div_raw(d10[j], c.div0, c.rdiv0), d10[j]);
+            q1[j] = copysign(markstein_div_raw(d32[j], c.div1, c.rdiv1), d32[j]);
+            ok = ok && exact_div_operand_ok(d10[j]) && (end || exact_div_operand_ok(d32[j]));
         }
         if (!ok) {
 #pragma unroll
@@ -502,6 +509,12 @@ __device__ __forceinline__ T quad4_reduce(const EvalArgs<T, N>& a, const T* __re
     }
 }
 
+// Measured and dropped (round 2, gpurun_out/r2_exp6): a software pipeline over groups of four first-level sectors — the
+// next group's loads issued as soon as the current group's sectors were reduced by their Horner polynomials, before its
+// run-time steps — needed 80 (regular) to 126 (rectilinear) registers and changed nothing: C2 30.7 against 30.5,
+// 3-D rectilinear 18.0 against 18.3, 4-D regular 8.76 against 8.51, 4-D rectilinear 5.79 against 6.06 G points/s. The
+// kernels are bound by the L2 -> L1 sector rate (C2, 4-D regular) or by issue + FP64 (rectilinear), not by the load latency
+// of one warp: the other resident warps already cover it.
 constexpr int kQuad4XposeQuad = 20;  // transposition buffer: element (node j, point p) of quad q at q*20 + 5j + p, see the kernel
 template <class T, int N, bool RECT>
 __host__ __device__ constexpr size_t quad4_smem_bytes() {  // beyond the staged axes

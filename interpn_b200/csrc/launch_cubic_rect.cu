@@ -50,9 +50,11 @@ cudaError_t launch_cubic_rect(const DeviceGrid& g, const T* const* obs, size_t n
                     else IB200_Q4R(3, 3);
                     break;
                 case 4:
+                    // measured (gpurun_out/r2_exp6, G points/s at 2 / 3 / 4 CTAs per SM): L2-resident 32^4 5.65 / 5.43 / 6.06,
+                    // C3-cubic through the bin-swept path 4.66 / 4.70 / 4.54
                     if (minb == 2) IB200_Q4R(4, 2);
-                    else if (minb == 4) IB200_Q4R(4, 4);
-                    else IB200_Q4R(4, 3);
+                    else if (minb == 3 || (minb == 0 && work != nullptr)) IB200_Q4R(4, 3);
+                    else IB200_Q4R(4, 4);
                     break;
                 default: break;
             }

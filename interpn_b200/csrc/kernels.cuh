@@ -69,6 +69,23 @@ __device__ __forceinline__ const T* stage_axes(const EvalArgs<T, N>& a) {
     return s;
 }
 
+// The same with the address space known at compile time: AXSM = the blob is staged and the returned pointer is a
+// shared-memory pointer the compiler can see through (every table access becomes LDS with 32-bit address arithmetic instead
+// of a generic load: the rectilinear streaming kernels spent a third of their stall samples behind generic loads,
+// profiles/r2_c5_n2rect_f32_ncu.json), else the global pointer. The kernels branch once on a.axes_in_smem.
+template <bool AXSM, class T, int N>
+__device__ __forceinline__ const T* stage_axes_as(const EvalArgs<T, N>& a) {
+    if constexpr (AXSM) {
+        extern __shared__ __align__(16) unsigned char smem_raw[];
+        T* s = reinterpret_cast<T*>(smem_raw);
+        for (int i = threadIdx.x; i < a.axes_total; i += blockDim.x) s[i] = a.axes[i];
+        __syncthreads();
+        return s;
+    } else {
+        return a.axes;
+    }
+}
+
 // partition_point(|g| g < x) on axis d. On strictly increasing axes a bucket table narrows the bisection to
 // the nodes of three adjacent buckets (two buckets per node on average): the computed bucket is within one of
 // the true one, lut[k] = partition_point(g < edge_k) is monotone in k, so the answer lies in
@@ -463,12 +480,12 @@ __device__ __forceinline__ bool nearest_locate_any(const EvalArgs<T, N>& a, cons
 // coordinate array, P independent locate/gather chains in flight, one vector store. The host picks
 // P > 1 only when every coordinate array and `out` are P*sizeof(T)-aligned (launch_common.cuh); the
 // n % P tail is evaluated one point per thread.
-template <class T, int N, bool RECT, int WL, int P, class I>
-__global__ void __launch_bounds__(kBlock) linear_kernel(const __grid_constant__ EvalArgs<T, N> a) {
+template <class T, int N, bool RECT, int WL, int P, class I, bool AXSM>
+__device__ __forceinline__ void linear_body(const EvalArgs<T, N>& a) {
     using O = Ops<T>;
     const I(&stride)[N] = strides_of<I>(a);
     const T* axes = nullptr;
-    if constexpr (RECT) axes = stage_axes<T, N>(a);
+    if constexpr (RECT) axes = stage_axes_as<AXSM, T, N>(a);
     const unsigned long long gtid = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     const unsigned long long ngroups = a.n / P;
     BlockSchedule sched;
@@ -520,6 +537,92 @@ __global__ void __launch_bounds__(kBlock) linear_kernel(const __grid_constant__ 
                 report_bad(a, i);
             }
         }
+    }
+}
+
+template <class T, int N, bool RECT, int WL, int P, class I>
+__global__ void __launch_bounds__(kBlock) linear_kernel(const __grid_constant__ EvalArgs<T, N> a) {
+    if constexpr (RECT) {
+        if (a.axes_in_smem) linear_body<T, N, RECT, WL, P, I, true>(a);
+        else linear_body<T, N, RECT, WL, P, I, false>(a);
+    } else {
+        linear_body<T, N, RECT, WL, P, I, false>(a);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 4-D multilinear on a grid beyond L2 (C3-linear): the hypercube layout, hwin[f*16 + v] = vals[f + sum_k bit_k(v)*stride_k]
+// — the whole 2^4 footprint of the cell at flat index f as ONE aligned 128-byte block (f64; 64 bytes in f32), a 16-fold
+// copy of the grid (C3: 2.1 GB). HBM serves random aligned 128-byte lines at 39 G/s = 5 TB/s when a line is ONE request
+// (four lanes, one LDG.256 each, in one instruction) against 50 G/s for 32-byte sectors requested separately
+// (profiles/r2_microbench_b200.json) — so a point costs one line instead of eight row gathers, no sort, no slab passes, and
+// the gather no longer sits on the L1 wavefront rate. (One thread loading its block with four instructions was measured at
+// 10.3 G points/s: the four sectors travel as four requests.)
+// Work split: thread i owns point i (coalesced coordinate loads, cell location, the last two lerp levels, coalesced store);
+// the quad works through its four points: lane j loads sector j of the point's block — bits (0,1) of v inside the sector,
+// bits (2,3) = j — and reduces dimensions 0 and 1 on it with the owner's t0, t1 (shuffles); the four partial results reach
+// the owner through the skewed transposition buffer of cubic_quad4.cuh. Every lerp and their order are the reference's.
+// ---------------------------------------------------------------------------------------------
+constexpr int kHyperXposeQuad = 20;
+template <class T>
+__host__ __device__ constexpr size_t linear_hyper4_smem_bytes() {
+    return static_cast<size_t>(kBlock / 32) * 8 * kHyperXposeQuad * sizeof(T);
+}
+
+template <class T, bool RECT, bool AXSM>
+__device__ __forceinline__ void linear_hyper4_body(const EvalArgs<T, 4>& a) {
+    using O = Ops<T>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const T* axes = nullptr;
+    size_t axes_bytes = 0;
+    if constexpr (RECT) {
+        axes = stage_axes_as<AXSM, T, 4>(a);
+        if constexpr (AXSM) axes_bytes = (static_cast<size_t>(a.axes_total) * sizeof(T) + 15) / 16 * 16;
+    }
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, j = lane & 3u, quad = lane >> 2;
+    const int qb = static_cast<int>(lane & ~3u);
+    T* xq = reinterpret_cast<T*>(smem_raw + axes_bytes) + (warp * 8 + quad) * kHyperXposeQuad;
+    const unsigned long long nblocks = (a.n + blockDim.x - 1) / blockDim.x;
+    for (unsigned long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const unsigned long long i = blk * blockDim.x + threadIdx.x;
+        const bool valid = i < a.n;
+        T xs[4];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) xs[d] = load_query(a.obs[d] + (valid ? i : a.n - 1));
+        T t[4];
+        int base;
+        const bool ok = linear_locate_any<T, 4, RECT, int, true>(a, axes, xs, t, base);
+        if (!ok) base = 0;  // keep the gather in range; the value is discarded
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int bp = __shfl_sync(0xffffffffu, base, qb + p);
+            const T t0 = __shfl_sync(0xffffffffu, t[0], qb + p), t1 = __shfl_sync(0xffffffffu, t[1], qb + p);
+            T v[4];
+            load_row<T, 4, true, long long>(nullptr, a.win, static_cast<long long>(bp) * 4 + j, v);
+            const T a0 = muladd(t0, O::sub(v[1], v[0]), v[0]);
+            const T a1 = muladd(t0, O::sub(v[3], v[2]), v[2]);
+            xq[j * 5 + p] = muladd(t1, O::sub(a1, a0), a0);
+        }
+        __syncwarp();
+        const T w0 = xq[j], w1 = xq[5 + j], w2 = xq[10 + j], w3 = xq[15 + j];  // this lane's point: the four sectors' results
+        __syncwarp();  // the next iteration overwrites the buffer
+        const T b0 = muladd(t[2], O::sub(w1, w0), w0);
+        const T b1 = muladd(t[2], O::sub(w3, w2), w2);
+        const T res = muladd(t[3], O::sub(b1, b0), b0);
+        if (valid) {
+            if (ok) store_result(a.out + i, res);
+            else report_bad(a, i);
+        }
+    }
+}
+
+template <class T, bool RECT>
+__global__ void __launch_bounds__(kBlock) linear_hyper4_kernel(const __grid_constant__ EvalArgs<T, 4> a) {
+    if constexpr (RECT) {
+        if (a.axes_in_smem) linear_hyper4_body<T, RECT, true>(a);
+        else linear_hyper4_body<T, RECT, false>(a);
+    } else {
+        linear_hyper4_body<T, RECT, false>(a);
     }
 }
 
@@ -606,10 +709,10 @@ __global__ void __launch_bounds__(kBlock, IB200_SLAB_MINB) linear_slab_kernel(co
 // Nearest (ref: nearest/regular.rs:234-295, nearest/rectilinear.rs:193-241)
 // ---------------------------------------------------------------------------------------------
 
-template <class T, int N, bool RECT, int P, class I>
-__global__ void __launch_bounds__(kBlock) nearest_kernel(const __grid_constant__ EvalArgs<T, N> a) {
+template <class T, int N, bool RECT, int P, class I, bool AXSM>
+__device__ __forceinline__ void nearest_body(const EvalArgs<T, N>& a) {
     const T* axes = nullptr;
-    if constexpr (RECT) axes = stage_axes<T, N>(a);
+    if constexpr (RECT) axes = stage_axes_as<AXSM, T, N>(a);
     const unsigned long long gstride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
     const unsigned long long gtid = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     const unsigned long long ngroups = a.n / P;
@@ -655,6 +758,16 @@ __global__ void __launch_bounds__(kBlock) nearest_kernel(const __grid_constant__
             if (nearest_locate_any<T, N, RECT, I>(a, axes, xs, idx)) store_result(a.out + i, __ldg(a.vals + idx));
             else report_bad(a, i);
         }
+    }
+}
+
+template <class T, int N, bool RECT, int P, class I>
+__global__ void __launch_bounds__(kBlock) nearest_kernel(const __grid_constant__ EvalArgs<T, N> a) {
+    if constexpr (RECT) {
+        if (a.axes_in_smem) nearest_body<T, N, RECT, P, I, true>(a);
+        else nearest_body<T, N, RECT, P, I, false>(a);
+    } else {
+        nearest_body<T, N, RECT, P, I, false>(a);
     }
 }
 

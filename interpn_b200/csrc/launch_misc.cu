@@ -33,6 +33,11 @@ __global__ void __launch_bounds__(kBlock) build_window_kernel(const T* __restric
     }
 }
 
+struct HyperDims {
+    int dim[kMaxNd];
+    long long stride[kMaxNd];
+};
+
 // Patch layout (kernels.cuh linear_patches): pwin[f*4 + 2*i + j] = vals[f + i*Db + j], with i and j dropped to 0 where
 // the patch would leave the grid (never read: a footprint origin is at most dim-2).
 template <class T>
@@ -50,8 +55,39 @@ __global__ void __launch_bounds__(kBlock) build_pwindow_kernel(const T* __restri
     }
 }
 
+// Hypercube layout (kernels.cuh linear_tree, WL = 2^N): hwin[f*2^N + v] = vals[f + sum_k bit_k(v)*stride_k]; offsets that
+// would leave the grid along a dimension are dropped (never read: a footprint origin is at most dim-2).
+template <class T>
+__global__ void __launch_bounds__(kBlock) build_hwindow_kernel(const T* __restrict__ vals, T* __restrict__ hwin,
+                                                               unsigned long long nvals, int ndims, const __grid_constant__ HyperDims hd) {
+    const unsigned long long total = nvals << ndims;
+    const unsigned long long gstride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+    for (unsigned long long k = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; k < total; k += gstride) {
+        const unsigned long long f = k >> ndims;
+        const unsigned v = static_cast<unsigned>(k) & ((1u << ndims) - 1u);
+        unsigned long long src = f;
+        for (int d = 0; d < ndims; ++d) {
+            const unsigned long long id = (f / static_cast<unsigned long long>(hd.stride[d])) % static_cast<unsigned long long>(hd.dim[d]);
+            if (((v >> d) & 1u) && id + 1 < static_cast<unsigned long long>(hd.dim[d])) src += static_cast<unsigned long long>(hd.stride[d]);
+        }
+        hwin[k] = vals[src];
+    }
+}
+
 cudaError_t launch_build_window(const DeviceGrid& g, cudaStream_t stream) {
     if (!g.win || g.nvals == 0) return cudaSuccess;
+    if (g.method == 0 && g.ndims >= 3 && g.win_width == (1 << g.ndims)) {  // INTERPN_B200_LINEAR, hypercube layout
+        HyperDims hd{};
+        for (int d = 0; d < g.ndims; ++d) {
+            hd.dim[d] = g.dim[d];
+            hd.stride[d] = g.stride[d];
+        }
+        const unsigned grid_dim = grid_for(g.nvals << g.ndims, g.sm_count, 8);
+        if (g.elem == 8) build_hwindow_kernel<double><<<grid_dim, kBlock, 0, stream>>>(static_cast<const double*>(g.vals), static_cast<double*>(g.win), g.nvals, g.ndims, hd);
+        else build_hwindow_kernel<float><<<grid_dim, kBlock, 0, stream>>>(static_cast<const float*>(g.vals), static_cast<float*>(g.win), g.nvals, g.ndims, hd);
+        count_launch();
+        return cudaGetLastError();
+    }
     const unsigned grid_dim = grid_for(g.nvals * g.win_width, g.sm_count, 8);
     if (g.win_cross && g.method == 0) {  // INTERPN_B200_LINEAR
         const unsigned long long da = g.dim[g.ndims - 2], db = g.dim[g.ndims - 1];

@@ -207,6 +207,44 @@ def test_slab_passes_bit_exact(ib, oracle, monkeypatch, ndims, dtype):
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("ndims", [4])
+def test_hypercube_layout_bit_exact(ib, oracle, monkeypatch, ndims, dtype):
+    """The hypercube layout of the multilinear kernels (kernels.cuh linear_hyper4_kernel: 4-D grids beyond L2, C3-linear)
+    forced onto small grids: every cell incl. the last one of each axis, points on nodes, outside the grid, and
+    unrepresentable points (regular) / NaN and infinities (rectilinear)."""
+    monkeypatch.setenv("INTERPN_B200_HYPER_MIN_KB", "0")
+    rng = np.random.default_rng(4471 + ndims)
+    n = 200_003
+    lo, hi = {3: (5, 12), 4: (4, 8), 5: (3, 6)}[ndims]
+    dims, grids, starts, steps, vals, obs = random_case(rng, ndims, n, lo, hi, dtype)
+    for d in range(ndims):  # exact nodes of every axis, the last one among them
+        obs[d][d * 64 : d * 64 + 64] = np.resize(grids[d], 64)
+    sfx = "f64" if dtype == np.float64 else "f32"
+    before = ib.launch_count()
+    out = np.zeros(n, dtype=dtype)
+    getattr(ib.raw, f"interpn_linear_regular_{sfx}")(dims, starts, steps, vals, obs, out)
+    assert_same_bits(out, oracle.interpn_regular("linear", dims, starts, steps, vals, obs, nthreads=8))
+    out = np.zeros(n, dtype=dtype)
+    getattr(ib.raw, f"interpn_linear_rectilinear_{sfx}")(grids, vals, obs, out)
+    assert_same_bits(out, oracle.interpn_rectilinear("linear", grids, vals, obs, nthreads=8))
+    assert ib.launch_count() >= before + 4, "expected a layout build and an evaluation launch per call"
+    bad = [n // 3, n // 3 + 5000, n // 2]
+    obs2 = [o.copy() for o in obs]
+    obs2[0][bad[0]] = np.nan
+    obs2[1][bad[1]] = np.inf
+    obs2[0][bad[2]] = -np.inf
+    out = np.full(n, -7.0, dtype=dtype)
+    with pytest.raises(AssertionError, match="Unrepresentable coordinate value"):
+        getattr(ib.raw, f"interpn_linear_regular_{sfx}")(dims, starts, steps, vals, obs2, out)
+    want = oracle.interpn_regular("linear", dims, starts, steps, vals, [o[: bad[0]] for o in obs], nthreads=8)
+    assert_same_bits(out[: bad[0]], want)
+    assert np.all(out[bad[0] :] == -7.0)
+    out = np.zeros(n, dtype=dtype)
+    getattr(ib.raw, f"interpn_linear_rectilinear_{sfx}")(grids, vals, obs2, out)
+    assert_same_bits(out, oracle.interpn_rectilinear("linear", grids, vals, obs2, nthreads=8))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_cubic_four_node_axes(ib, oracle, dtype):
     """Axes with exactly 4 nodes: origin is always 0 and every saturation class is reachable
     (SURVEY.md appendix A)."""

@@ -256,6 +256,14 @@ int main() {
         printf(", \"row32B_ldg256_L2_Grows_s\": %.2f, \"row4x_ldg64_L2_Grows_s\": %.2f, \"row2x_ldg128_L2_Grows_s\": %.2f"
                ", \"pair_ldg128_L2_Gloads_s\": %.2f, \"ldg64_L2_Gloads_s\": %.2f, \"ldg64_L1hit_Gloads_s\": %.2f, \"ldg256_L1hit_Grows_s\": %.2f",
                rows / t0 * 1e-6, rows / t1 * 1e-6, rows / t2 * 1e-6, rows / t3 * 1e-6, rows / t4 * 1e-6, rows / t5 * 1e-6, rows / t6 * 1e-6);
+        {   // the same from HBM: 128-byte lines at random from a 2 GB table (16-value hypercube blocks of a 4-D multilinear grid)
+            const size_t big_sectors = size_t(1) << 26;  // 2 GiB
+            double* big; CK(cudaMalloc(&big, big_sectors * 32)); CK(cudaMemset(big, 0, big_sectors * 32));
+            float h1 = time_ms([&] { quad_gather_kernel<1><<<blocks, threads>>>(big, unsigned(big_sectors), per, out); });
+            float h0 = time_ms([&] { quad_gather_kernel<0><<<blocks, threads>>>(big, unsigned(big_sectors), per, out); });
+            printf(", \"quad128B_aligned_hbm_Glines_s\": %.2f, \"quad128B_unaligned_hbm_Gquads_s\": %.2f", rows / 4 / h1 * 1e-6, rows / 4 / h0 * 1e-6);
+            CK(cudaFree(big));
+        }
         float q0 = time_ms([&] { quad_gather_kernel<0><<<blocks, threads>>>(tab, n32 / 4, per, out); });
         float q1 = time_ms([&] { quad_gather_kernel<1><<<blocks, threads>>>(tab, n32 / 4, per, out); });
         printf(", \"quad128B_ldg256_L2_Gsectors_s\": %.2f, \"quad128B_aligned_ldg256_L2_Gsectors_s\": %.2f", rows / q0 * 1e-6, rows / q1 * 1e-6);

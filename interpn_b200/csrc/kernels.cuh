@@ -551,32 +551,38 @@ __global__ void __launch_bounds__(kBlock) linear_kernel(const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------
-// 4-D multilinear on a grid beyond L2 (C3-linear): the hypercube layout, hwin[f*16 + v] = vals[f + sum_k bit_k(v)*stride_k]
-// — the whole 2^4 footprint of the cell at flat index f as ONE aligned 128-byte block (f64; 64 bytes in f32), a 16-fold
-// copy of the grid (C3: 2.1 GB). HBM serves random aligned 128-byte lines at 39 G/s = 5 TB/s when a line is ONE request
-// (four lanes, one LDG.256 each, in one instruction) against 50 G/s for 32-byte sectors requested separately
-// (profiles/r2_microbench_b200.json) — so a point costs one line instead of eight row gathers, no sort, no slab passes, and
-// the gather no longer sits on the L1 wavefront rate. (One thread loading its block with four instructions was measured at
-// 10.3 G points/s: the four sectors travel as four requests.)
+// Multilinear N = 4..6 on a grid beyond L2 (C3-linear, C4): the hypercube layout,
+//   hwin[f*16 + v] = vals[f + sum_b bit_b(v) * stride_{N-4+b}],
+// — the 2^4 corners of the cell at flat index f over the LAST FOUR dimensions as one aligned 128-byte block (f64; 64 bytes
+// in f32), a 16-fold copy of the grid (C3: 2.1 GB, C4: 24.5 GB; 180 GB of HBM is what it is for). HBM serves random aligned
+// 128-byte lines at 39 G/s = 5 TB/s when a line is ONE request — four lanes, one LDG.256 each, in one instruction — against
+// 50 G/s for 32-byte sectors requested separately (profiles/r2_microbench_b200.json). A point therefore costs 2^(N-4) line
+// requests (the corners of the leading dimensions) instead of 2^(N-1) row gathers: no sort, no slab passes, and the
+// gather no longer sits on the L1 wavefront rate. (One thread loading its block with four instructions was measured
+// at 10.3 G points/s on C3-linear: the four sectors travel as four requests.)
 // Work split: thread i owns point i (coalesced coordinate loads, cell location, the last two lerp levels, coalesced store);
-// the quad works through its four points: lane j loads sector j of the point's block — bits (0,1) of v inside the sector,
-// bits (2,3) = j — and reduces dimensions 0 and 1 on it with the owner's t0, t1 (shuffles); the four partial results reach
-// the owner through the skewed transposition buffer of cubic_quad4.cuh. Every lerp and their order are the reference's.
+// the quad works through its four points: lane j loads sector j of each of the point's blocks — bits (0,1) of v, i.e.
+// dimensions N-4 and N-3, inside the sector; bits (2,3) = j, dimensions N-2 and N-1 — reduces the leading dimensions
+// between the blocks (dimension 0 first) and then dimensions N-4, N-3 inside the sector, with the owner's t (shuffles); the
+// four partial results reach the owner through the skewed transposition buffer of cubic_quad4.cuh, and the owner finishes
+// with dimensions N-2 and N-1. Every lerp and their order are the reference's (multilinear/regular.rs:362-388).
 // ---------------------------------------------------------------------------------------------
 constexpr int kHyperXposeQuad = 20;
 template <class T>
-__host__ __device__ constexpr size_t linear_hyper4_smem_bytes() {
+__host__ __device__ constexpr size_t linear_hyper_smem_bytes() {
     return static_cast<size_t>(kBlock / 32) * 8 * kHyperXposeQuad * sizeof(T);
 }
 
-template <class T, bool RECT, bool AXSM>
-__device__ __forceinline__ void linear_hyper4_body(const EvalArgs<T, 4>& a) {
+template <class T, int N, bool RECT, bool AXSM>
+__device__ __forceinline__ void linear_hyper_body(const EvalArgs<T, N>& a) {
+    static_assert(N >= 4 && N <= 6, "the hypercube layout covers N = 4..6");
     using O = Ops<T>;
+    constexpr int L = N - 4;  // leading dimensions: 2^L blocks per point
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const T* axes = nullptr;
     size_t axes_bytes = 0;
     if constexpr (RECT) {
-        axes = stage_axes_as<AXSM, T, 4>(a);
+        axes = stage_axes_as<AXSM, T, N>(a);
         if constexpr (AXSM) axes_bytes = (static_cast<size_t>(a.axes_total) * sizeof(T) + 15) / 16 * 16;
     }
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, j = lane & 3u, quad = lane >> 2;
@@ -586,29 +592,46 @@ __device__ __forceinline__ void linear_hyper4_body(const EvalArgs<T, 4>& a) {
     for (unsigned long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
         const unsigned long long i = blk * blockDim.x + threadIdx.x;
         const bool valid = i < a.n;
-        T xs[4];
+        T xs[N];
 #pragma unroll
-        for (int d = 0; d < 4; ++d) xs[d] = load_query(a.obs[d] + (valid ? i : a.n - 1));
-        T t[4];
+        for (int d = 0; d < N; ++d) xs[d] = load_query(a.obs[d] + (valid ? i : a.n - 1));
+        T t[N];
         int base;
-        const bool ok = linear_locate_any<T, 4, RECT, int, true>(a, axes, xs, t, base);
+        const bool ok = linear_locate_any<T, N, RECT, int, true>(a, axes, xs, t, base);
         if (!ok) base = 0;  // keep the gather in range; the value is discarded
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
             const int bp = __shfl_sync(0xffffffffu, base, qb + p);
-            const T t0 = __shfl_sync(0xffffffffu, t[0], qb + p), t1 = __shfl_sync(0xffffffffu, t[1], qb + p);
-            T v[4];
-            load_row<T, 4, true, long long>(nullptr, a.win, static_cast<long long>(bp) * 4 + j, v);
-            const T a0 = muladd(t0, O::sub(v[1], v[0]), v[0]);
-            const T a1 = muladd(t0, O::sub(v[3], v[2]), v[2]);
-            xq[j * 5 + p] = muladd(t1, O::sub(a1, a0), a0);
+            T tp[L + 2];  // the owner's t of the leading dimensions and of the two in-sector dimensions
+#pragma unroll
+            for (int d = 0; d < L + 2; ++d) tp[d] = __shfl_sync(0xffffffffu, t[d], qb + p);
+            T v[1 << L][4];
+#pragma unroll
+            for (int c = 0; c < (1 << L); ++c) {
+                int off = 0;
+#pragma unroll
+                for (int d = 0; d < L; ++d) off += ((c >> d) & 1) ? a.istride[d] : 0;
+                load_row<T, 4, true, long long>(nullptr, a.win, static_cast<long long>(bp + off) * 4 + j, v[c]);
+            }
+            // leading dimensions between the blocks, dimension 0 (bit 0 of c) first
+#pragma unroll
+            for (int d = 0; d < L; ++d) {
+#pragma unroll
+                for (int c = 0; c < ((1 << L) >> (d + 1)); ++c) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) v[c][e] = muladd(tp[d], O::sub(v[2 * c + 1][e], v[2 * c][e]), v[2 * c][e]);
+                }
+            }
+            const T a0 = muladd(tp[L], O::sub(v[0][1], v[0][0]), v[0][0]);
+            const T a1 = muladd(tp[L], O::sub(v[0][3], v[0][2]), v[0][2]);
+            xq[j * 5 + p] = muladd(tp[L + 1], O::sub(a1, a0), a0);
         }
         __syncwarp();
         const T w0 = xq[j], w1 = xq[5 + j], w2 = xq[10 + j], w3 = xq[15 + j];  // this lane's point: the four sectors' results
         __syncwarp();  // the next iteration overwrites the buffer
-        const T b0 = muladd(t[2], O::sub(w1, w0), w0);
-        const T b1 = muladd(t[2], O::sub(w3, w2), w2);
-        const T res = muladd(t[3], O::sub(b1, b0), b0);
+        const T b0 = muladd(t[N - 2], O::sub(w1, w0), w0);
+        const T b1 = muladd(t[N - 2], O::sub(w3, w2), w2);
+        const T res = muladd(t[N - 1], O::sub(b1, b0), b0);
         if (valid) {
             if (ok) store_result(a.out + i, res);
             else report_bad(a, i);
@@ -616,13 +639,13 @@ __device__ __forceinline__ void linear_hyper4_body(const EvalArgs<T, 4>& a) {
     }
 }
 
-template <class T, bool RECT>
-__global__ void __launch_bounds__(kBlock) linear_hyper4_kernel(const __grid_constant__ EvalArgs<T, 4> a) {
+template <class T, int N, bool RECT>
+__global__ void __launch_bounds__(kBlock) linear_hyper_kernel(const __grid_constant__ EvalArgs<T, N> a) {
     if constexpr (RECT) {
-        if (a.axes_in_smem) linear_hyper4_body<T, RECT, true>(a);
-        else linear_hyper4_body<T, RECT, false>(a);
+        if (a.axes_in_smem) linear_hyper_body<T, N, RECT, true>(a);
+        else linear_hyper_body<T, N, RECT, false>(a);
     } else {
-        linear_hyper4_body<T, RECT, false>(a);
+        linear_hyper_body<T, N, RECT, false>(a);
     }
 }
 

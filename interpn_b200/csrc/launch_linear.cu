@@ -36,13 +36,13 @@ cudaError_t launch_linear_n(const DeviceGrid& g, const T* const* obs, size_t n, 
     // Window copy (capi.cu window_width): row pairs (N = 1, and small grids whose 2-fold copy still fits L1), else 2x2
     // patches of the last two dimensions.
     constexpr int kPatch = N >= 2 ? 4 : 2;
-    if constexpr (N == 4) {  // grids beyond L2: one aligned block per point from the hypercube layout (capi.cu window_width)
+    if constexpr (N >= 4 && N <= 6) {  // grids beyond L2: 2^(N-4) aligned blocks per point from the hypercube layout (capi.cu window_width)
         if (g.win != nullptr && g.win_width == 16 && !index64(g)) {
             LaunchOpts o;
             o.window = true;
-            o.extra_smem = linear_hyper4_smem_bytes<T>();
+            o.extra_smem = linear_hyper_smem_bytes<T>();
             o.ctas_per_sm = static_cast<int>(sweep_env("INTERPN_B200_HYPER_CTAS", 8));
-            return launch_generic<T, 4>(linear_hyper4_kernel<T, RECT>, g, obs, n, out, first_bad, index_base, stream, o);
+            return launch_generic<T, N>(linear_hyper_kernel<T, N, RECT>, g, obs, n, out, first_bad, index_base, stream, o);
         }
     }
     const bool has_patch = kCanWin && g.win != nullptr && g.win_width == kPatch;

@@ -55,20 +55,21 @@ __global__ void __launch_bounds__(kBlock) build_pwindow_kernel(const T* __restri
     }
 }
 
-// Hypercube layout (kernels.cuh linear_tree, WL = 2^N): hwin[f*2^N + v] = vals[f + sum_k bit_k(v)*stride_k]; offsets that
-// would leave the grid along a dimension are dropped (never read: a footprint origin is at most dim-2).
+// Hypercube layout (kernels.cuh linear_hyper_kernel): hwin[f*16 + v] = vals[f + sum_b bit_b(v)*stride_{N-4+b}]; offsets
+// that would leave the grid along a dimension are dropped (never read: a footprint origin is at most dim-2).
 template <class T>
 __global__ void __launch_bounds__(kBlock) build_hwindow_kernel(const T* __restrict__ vals, T* __restrict__ hwin,
-                                                               unsigned long long nvals, int ndims, const __grid_constant__ HyperDims hd) {
-    const unsigned long long total = nvals << ndims;
+                                                               unsigned long long nvals, const __grid_constant__ HyperDims hd) {
+    const unsigned long long total = nvals << 4;
     const unsigned long long gstride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
     for (unsigned long long k = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; k < total; k += gstride) {
-        const unsigned long long f = k >> ndims;
-        const unsigned v = static_cast<unsigned>(k) & ((1u << ndims) - 1u);
+        const unsigned long long f = k >> 4;
+        const unsigned v = static_cast<unsigned>(k) & 15u;
         unsigned long long src = f;
-        for (int d = 0; d < ndims; ++d) {
-            const unsigned long long id = (f / static_cast<unsigned long long>(hd.stride[d])) % static_cast<unsigned long long>(hd.dim[d]);
-            if (((v >> d) & 1u) && id + 1 < static_cast<unsigned long long>(hd.dim[d])) src += static_cast<unsigned long long>(hd.stride[d]);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {  // hd holds the last four dimensions
+            const unsigned long long id = (f / static_cast<unsigned long long>(hd.stride[b])) % static_cast<unsigned long long>(hd.dim[b]);
+            if (((v >> b) & 1u) && id + 1 < static_cast<unsigned long long>(hd.dim[b])) src += static_cast<unsigned long long>(hd.stride[b]);
         }
         hwin[k] = vals[src];
     }
@@ -76,15 +77,15 @@ __global__ void __launch_bounds__(kBlock) build_hwindow_kernel(const T* __restri
 
 cudaError_t launch_build_window(const DeviceGrid& g, cudaStream_t stream) {
     if (!g.win || g.nvals == 0) return cudaSuccess;
-    if (g.method == 0 && g.ndims >= 3 && g.win_width == (1 << g.ndims)) {  // INTERPN_B200_LINEAR, hypercube layout
+    if (g.method == 0 && g.ndims >= 4 && g.win_width == 16) {  // INTERPN_B200_LINEAR, hypercube layout
         HyperDims hd{};
-        for (int d = 0; d < g.ndims; ++d) {
-            hd.dim[d] = g.dim[d];
-            hd.stride[d] = g.stride[d];
+        for (int b = 0; b < 4; ++b) {
+            hd.dim[b] = g.dim[g.ndims - 4 + b];
+            hd.stride[b] = g.stride[g.ndims - 4 + b];
         }
-        const unsigned grid_dim = grid_for(g.nvals << g.ndims, g.sm_count, 8);
-        if (g.elem == 8) build_hwindow_kernel<double><<<grid_dim, kBlock, 0, stream>>>(static_cast<const double*>(g.vals), static_cast<double*>(g.win), g.nvals, g.ndims, hd);
-        else build_hwindow_kernel<float><<<grid_dim, kBlock, 0, stream>>>(static_cast<const float*>(g.vals), static_cast<float*>(g.win), g.nvals, g.ndims, hd);
+        const unsigned grid_dim = grid_for(g.nvals << 4, g.sm_count, 8);
+        if (g.elem == 8) build_hwindow_kernel<double><<<grid_dim, kBlock, 0, stream>>>(static_cast<const double*>(g.vals), static_cast<double*>(g.win), g.nvals, hd);
+        else build_hwindow_kernel<float><<<grid_dim, kBlock, 0, stream>>>(static_cast<const float*>(g.vals), static_cast<float*>(g.win), g.nvals, hd);
         count_launch();
         return cudaGetLastError();
     }

@@ -46,6 +46,7 @@ SWEEP = {"INTERPN_B200_SWEEP_MIN_MB": "0", "INTERPN_B200_SWEEP_MIN_POINTS": "0",
          "INTERPN_B200_SWEEP_SLAB_KB": "0", "INTERPN_B200_SWEEP_CHUNK": "20000"}  # fmt: skip
 SLAB = {"INTERPN_B200_WINDOW_MB": "0", "INTERPN_B200_SLAB_MIN_KB": "0", "INTERPN_B200_SLAB_MIN_POINTS": "0", "INTERPN_B200_SLAB_PASS_KB": "2"}
 WIN = {"INTERPN_B200_WINDOW_MIN_KB": "0"}
+HYPER = {"INTERPN_B200_HYPER_MIN_KB": "0"}
 PLAIN = {"INTERPN_B200_WINDOW_MB": "0"}
 
 n0 = ib.launch_count()
@@ -54,7 +55,7 @@ for dtype in (np.float64, np.float32):
     for method, nds in (("linear", (1, 2, 3, 4, 6, 8)), ("cubic", (1, 2, 3, 4, 5)), ("nearest", (1, 2, 3, 6))):
         for nd in nds:
             n = 3001 if not (method == "cubic" and nd >= 4) else 601
-            run(method, nd, dtype, n, WIN)   # window / patch / cross-window layouts, quad4 kernels
+            run(method, nd, dtype, n, WIN)   # window / patch / coefficient layouts, quad4 kernels
             run(method, nd, dtype, n, PLAIN)  # straight from vals
             cases += 2
     for method, nd in (("linear", 3), ("linear", 6), ("cubic", 2), ("cubic", 3), ("cubic", 4)):
@@ -62,6 +63,9 @@ for dtype in (np.float64, np.float32):
         cases += 1
     for nd in (3, 4, 5):
         run("linear", nd, dtype, 30_011, SLAB, maxdim={3: 14, 4: 8, 5: 6}[nd])  # warp-compacting slab passes
+        cases += 1
+    for nd in (4, 5, 6):
+        run("linear", nd, dtype, 9001, HYPER)  # quad-cooperative hypercube kernels (shared-memory transposition behind __syncwarp)
         cases += 1
     run("linear", 3, dtype, 3001, {"INTERPN_B200_INDEX64": "1"})
     run("nearest", 3, dtype, 3001, {"INTERPN_B200_INDEX64": "1"})

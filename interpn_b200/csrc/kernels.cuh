@@ -739,15 +739,39 @@ __device__ __forceinline__ void nearest_body(const EvalArgs<T, N>& a) {
     const unsigned long long gstride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
     const unsigned long long gtid = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     const unsigned long long ngroups = a.n / P;
+    // The coordinates of the thread's NEXT group are requested before the current group is located and gathered, so their
+    // DRAM latency overlaps the search / gather / store chain (ncu on 2-D rectilinear f32: 17 long-scoreboard stall cycles
+    // per issue at 33 % issue activity — each iteration began with a full DRAM round trip, profiles/r2_c5_n2rect_f32_ncu.json).
+    // Measured (gpurun_out/r2_exp8, G points/s with / without): regular 2-D 198 / 194 (f32 229 / 221), 3-D 173 / 161 (f32 214 /
+    // 208), rectilinear f32 2-D 96.6 / 87.7, 3-D 126.6 / 122.8 — but rectilinear f64 114 / 128 and 93 / 104 (the extra
+    // registers cost it a resident CTA), which therefore keeps the plain loop.
+    constexpr bool kPrefetch = !(RECT && sizeof(T) == 8);
+    T nx[N][P];
+    if (kPrefetch && gtid < ngroups) {
+#pragma unroll
+        for (int d = 0; d < N; ++d) load_query_vec<T, P>(a.obs[d] + gtid * P, nx[d]);
+    }
     for (unsigned long long g = gtid; g < ngroups; g += gstride) {
         const unsigned long long i0 = g * P;
         T xs[P][N];
+        if constexpr (kPrefetch) {
 #pragma unroll
-        for (int d = 0; d < N; ++d) {
-            T v[P];
-            load_query_vec<T, P>(a.obs[d] + i0, v);
+            for (int d = 0; d < N; ++d) {
 #pragma unroll
-            for (int p = 0; p < P; ++p) xs[p][d] = v[p];
+                for (int p = 0; p < P; ++p) xs[p][d] = nx[d][p];
+            }
+            if (g + gstride < ngroups) {
+#pragma unroll
+                for (int d = 0; d < N; ++d) load_query_vec<T, P>(a.obs[d] + (g + gstride) * P, nx[d]);
+            }
+        } else {
+#pragma unroll
+            for (int d = 0; d < N; ++d) {
+                T v[P];
+                load_query_vec<T, P>(a.obs[d] + i0, v);
+#pragma unroll
+                for (int p = 0; p < P; ++p) xs[p][d] = v[p];
+            }
         }
         I idx[P];
         bool ok[P];

@@ -213,13 +213,6 @@ int upload_vals(interpn_b200_interp* h, const void* vals, int vals_location) {
 
 int finish_new(interpn_b200_interp* h) {
     CUDA_TRY(cudaGetDevice(&h->device));
-    // The bin-swept kernels take their scratch from the stream-ordered default pool: keep it cached.
-    cudaMemPool_t pool = nullptr;
-    if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess) {
-        uint64_t keep = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-    cudaGetLastError();
     CUDA_TRY(cudaMalloc(&h->first_bad_dev, sizeof(unsigned long long)));
     CUDA_TRY(cudaMemset(h->first_bad_dev, 0xff, sizeof(unsigned long long)));
     return INTERPN_B200_OK;
@@ -570,12 +563,6 @@ int ensure_replicas(interpn_b200_interp* h, int want) {
             CUDA_TRY(cudaMalloc(&r->g.axes, static_cast<size_t>(g.axes_total) * g.elem));
             CUDA_TRY(cudaMemcpyPeer(r->g.axes, dev, g.axes, h->device, static_cast<size_t>(g.axes_total) * g.elem));
         }
-        cudaMemPool_t pool = nullptr;
-        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            uint64_t keep = UINT64_MAX;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-        cudaGetLastError();
         CUDA_TRY(cudaDeviceSynchronize());
     }
     CUDA_TRY(cudaSetDevice(h->device));

@@ -1,5 +1,6 @@
 // launch_misc.cu — one_dim evaluators, check_bounds, and the method dispatcher.
 #include <cstdlib>
+#include <mutex>
 
 #include "launch_common.cuh"
 
@@ -11,6 +12,29 @@ size_t sweep_env(const char* name, size_t fallback) {
 }
 
 size_t sweep_env_common(const char* name, size_t fallback) { return sweep_env(name, fallback); }
+
+cudaMemPool_t sweep_scratch_pool() {
+    static cudaMemPool_t pools[64] = {};
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!pools[dev]) {
+        cudaMemPoolProps props{};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        if (cudaMemPoolCreate(&pools[dev], &props) != cudaSuccess) {
+            cudaGetLastError();
+            cudaDeviceGetDefaultMemPool(&pools[dev], dev);  // fall back to the default pool, untouched
+        } else {
+            uint64_t keep = UINT64_MAX;  // keep the scratch cached between calls (several GB for C3-cubic)
+            cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
+    return pools[dev];
+}
 
 bool force_index64() {
     const char* e = getenv("INTERPN_B200_INDEX64");

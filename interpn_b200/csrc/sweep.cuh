@@ -315,6 +315,9 @@ __global__ void __launch_bounds__(kBlock) sweep_unsort_kernel(const __grid_const
 // ---------------------------------------------------------------------------------------------
 
 size_t sweep_env(const char* name, size_t fallback);
+// The library's own stream-ordered memory pool on the current device (launch_misc.cu): the sweep scratch is cached there
+// between calls, so the process-wide default pool — which torch, RMM or cuDF may share — keeps its own release policy.
+cudaMemPool_t sweep_scratch_pool();
 
 // Decide whether `n` points on grid `g` are worth sweeping and fill the key description. `fp` is the
 // footprint width (2 linear, 4 cubic); `row_bytes_scale` the blow-up of the array the kernel gathers
@@ -403,11 +406,11 @@ inline cudaError_t launch_sweep(const DeviceGrid& g, int fp, int row_bytes_scale
     if (chunk > n) chunk = n;
     const size_t chunk_al = (chunk + 63) / 64 * 64;
 
-    // Stream-ordered scratch from the device's default pool (kept cached between calls, capi.cu finish_new).
+    // Stream-ordered scratch from the library's own pool (kept cached between calls, launch_misc.cu sweep_scratch_pool).
     const size_t bytes = chunk_al * ((N + 1) * sizeof(T) + 2 * sizeof(unsigned) + sizeof(unsigned short)) +
                          static_cast<size_t>(key.nbins) * kSweepSlots * sizeof(unsigned) + 64;
     void* scratch = nullptr;
-    e = cudaMallocAsync(&scratch, bytes, stream);
+    e = cudaMallocFromPoolAsync(&scratch, bytes, sweep_scratch_pool(), stream);
     if (e != cudaSuccess) {
         cudaGetLastError();
         return cudaSuccess;  // no memory for the scratch: the direct kernel takes the call

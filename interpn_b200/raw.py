@@ -8,6 +8,12 @@ function's dtype (the PyO3 extractors reject anything else with TypeError); ever
 arrays: each call copies the grid and the query batch to the GPU, evaluates there, and copies
 the result into ``out``. For repeated evaluation on one grid or for device-resident data use
 ``interpn_b200.Interpolator`` (the grid stays in HBM).
+
+Arithmetic flavour. The reference exists in two builds that differ by a few ulp: the crate's default
+features (every ``a*b + c`` rounded twice) and its ``fma`` feature — the build of the published Python
+wheel (pyproject.toml:72). This package follows the CRATE by default (``libinterpn_b200.so``); a Python
+user who wants the wheel's bits sets ``INTERPN_B200_ARITHMETIC=fma`` before the first import
+(``libinterpn_b200_fma.so``, bit-identical to the wheel's own outputs on tests/golden/ref_docs.npz).
 """
 
 from __future__ import annotations

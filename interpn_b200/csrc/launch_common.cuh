@@ -14,7 +14,7 @@ size_t sweep_env_common(const char* name, size_t fallback);
 // True when the kernels stage the rectilinear axes blob in shared memory (INTERPN_B200_AXES_SMEM_KB overrides the budget).
 template <class T>
 inline bool axes_fit_smem(const DeviceGrid& g) {
-    static const size_t axes_budget = sweep_env_common("INTERPN_B200_AXES_SMEM_KB", kAxesSmemBudget >> 10) << 10;
+    const size_t axes_budget = sweep_env_common("INTERPN_B200_AXES_SMEM_KB", kAxesSmemBudget >> 10) << 10;  // read per call (tests)
     return g.rect && static_cast<size_t>(g.axes_total) * sizeof(T) <= axes_budget;
 }
 

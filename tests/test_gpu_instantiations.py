@@ -293,3 +293,33 @@ def test_rectilinear_axes_whose_span_leaves_the_bucket_tables_range(ib, oracle, 
     want = oracle.interpn_rectilinear(method, grids, vals, obs, linearize_extrapolation=True, nthreads=4)
     both_nan = np.isnan(out) & np.isnan(want)
     assert np.all((out.view(np.uint32) == want.view(np.uint32)) | both_nan)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("method,ndims", [("linear", 2), ("linear", 4), ("linear", 6), ("nearest", 2), ("nearest", 3),
+                                          ("cubic", 2), ("cubic", 3), ("cubic", 4)])  # fmt: skip
+def test_rectilinear_axes_in_global_memory_bit_exact(ib, oracle, monkeypatch, method, ndims, dtype):
+    """Every rectilinear kernel exists twice: with the axes blob (axes, bucket / cell tables) staged in shared memory and
+    with the blob read from global memory (blobs beyond the 96 KB budget). INTERPN_B200_AXES_SMEM_KB=0 forces the second
+    instantiation onto small grids — incl. the quad-cooperative cubic kernels and the hypercube multilinear kernels — and a
+    2-D grid with 3 000-node axes takes it for real."""
+    monkeypatch.setenv("INTERPN_B200_AXES_SMEM_KB", "0")
+    monkeypatch.setenv("INTERPN_B200_HYPER_MIN_KB", "0")
+    rng = np.random.default_rng(8123 + ndims)
+    n = 60_007
+    lo = 4 if method == "cubic" else 2
+    hi = {2: 40, 3: 12, 4: 8, 6: 5}[ndims]
+    dims, grids, starts, steps, vals, obs = random_case(rng, ndims, n, lo, hi, dtype)
+    sfx = "f64" if dtype == np.float64 else "f32"
+    extra = (True,) if method == "cubic" else ()
+    out = np.zeros(n, dtype=dtype)
+    getattr(ib.raw, f"interpn_{method}_rectilinear_{sfx}")(grids, vals, *extra, obs, out)
+    assert_same_bits(out, oracle.interpn_rectilinear(method, grids, vals, obs, linearize_extrapolation=True, nthreads=8))
+    if ndims == 2:  # axes too long for shared memory without any hook
+        monkeypatch.delenv("INTERPN_B200_AXES_SMEM_KB")
+        big = [np.cumsum(rng.random(3000) + 0.05).astype(dtype) for _ in range(2)]
+        bvals = rng.standard_normal(3000 * 3000).astype(dtype)
+        bobs = [(rng.random(n) * (g[-1] - g[0]) * 1.1 + g[0] - 0.05 * (g[-1] - g[0])).astype(dtype) for g in big]
+        out = np.zeros(n, dtype=dtype)
+        getattr(ib.raw, f"interpn_{method}_rectilinear_{sfx}")(big, bvals, *extra, bobs, out)
+        assert_same_bits(out, oracle.interpn_rectilinear(method, big, bvals, bobs, linearize_extrapolation=True, nthreads=8))

@@ -113,6 +113,33 @@ def ncu_traffic(workload: str, dtype: str, n: int):
     return None, None
 
 
+# The unit that actually binds each workload's dominant kernel, as (microbenchmark key in
+# profiles/r2_microbench_b200.json, units per query point, description). Reported next to the HBM roofline as
+# roofline.binding = {unit, per_point, measured_peak, frac}: how close the kernel is to the ceiling of what it has to move.
+BINDING = {
+    "c2_cubic3d_reg100": ("quad128B_ldg256_L2_Gsectors_s", 16.75, "L2 -> L1 32-byte sectors (16 coefficient sectors + coordinates per point)"),
+    "c3_cubic4d_rect64": ("quad128B_ldg256_L2_Gsectors_s", 65.0, "L2 -> L1 32-byte sectors (64 coefficient sectors + coordinates per point)"),
+    "c3_linear4d_rect64": ("quad128B_aligned_hbm_Glines_s", 1.0, "random aligned 128-byte lines from HBM (one hypercube block per point)"),
+    "c4_linear6d_reg24": ("quad128B_aligned_hbm_Glines_s", 4.0, "random aligned 128-byte lines from HBM (four hypercube blocks per point)"),
+    "c1_linear3d_reg20": ("pair_ldg128_L2_Gloads_s", 4.0, "L1 wavefronts of lone gathers (four row pairs per point)"),
+    "c5_nearest2d_reg1024": ("gather8B_random_Gloads_s", 1.0, "L1 wavefronts of lone gathers (one node per point)"),
+    "c5_nearest3d_reg128": ("gather8B_random_Gloads_s", 1.0, "L1 wavefronts of lone gathers (one node per point)"),
+    "c5_nearest2d_rect1024": ("gather8B_random_Gloads_s", 1.0, "L1 wavefronts of lone gathers (one node per point; the axis search adds shared-memory wavefronts)"),
+    "c5_nearest3d_rect128": ("gather8B_random_Gloads_s", 1.0, "L1 wavefronts of lone gathers (one node per point; the axis search adds shared-memory wavefronts)"),
+}
+
+
+def binding_ceiling(workload: str, points_per_s_per_gpu: float):
+    try:
+        key, per_point, what = BINDING[workload]
+        with open(os.path.join(ROOT, "profiles", "r2_microbench_b200.json")) as f:
+            peak = float(json.load(f)[key]) * 1e9
+        return {"unit": what, "per_point": per_point, "measured_peak_per_s": peak, "source": f"profiles/r2_microbench_b200.json {key}",
+                "frac": points_per_s_per_gpu * per_point / peak}
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU baseline (oracle) — also the whole of the `--impl reference` arm
 # ------------------------------------------------------------------------------------------------
@@ -516,6 +543,7 @@ def measure(cx: Ctx, name: str, dtype: str, n: int, steps: int, warmup: int, sus
                        "algorithmic bytes per step over the step's device time"),
             "algorithmic_bytes_per_launch": abytes,
             "kernel_ms": mean_ms,
+            "binding": binding_ceiling(w.name, n * per_step_launches / (mean_ms * 1e-3)),
         },
         "gpu_launches": int(launches),
         "swept_launches": int(swept),

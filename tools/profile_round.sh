@@ -32,9 +32,9 @@ full x4reg_coef x_cubic4d_reg32 f64 50000000 cubic_quad4 3 1
 full x3rect_coef x_cubic3d_rect100 f64 50000000 cubic_quad4 3 1
 full x4rect_coef x_cubic4d_rect32 f64 30000000 cubic_quad4 3 1
 full c3c_coef c3_cubic4d_rect64 f64 100000000 cubic_quad4 12 1
-full c3l_slab c3_linear4d_rect64 f64 100000000 linear_slab 9 3
-full c4_eval c4_linear6d_reg24 f64 125000000 linear_kernel 3 1
-full c4_scatter c4_linear6d_reg24 f64 125000000 sweep_scatter 3 1
+full c3l_hyper c3_linear4d_rect64 f64 100000000 linear_hyper 3 1
+full c4_hyper c4_linear6d_reg24 f64 125000000 linear_hyper 3 1
+full c3c_scatter c3_cubic4d_rect64 f64 100000000 sweep_scatter 3 1
 full c5_n2rect_f32 c5_nearest2d_rect1024 f32 200000000 nearest_kernel 3 1
 full c5_n3reg_f64 c5_nearest3d_reg128 f64 200000000 nearest_kernel 3 1
 full c1_linear c1_linear3d_reg20 f64 1000000 linear_kernel 3 1

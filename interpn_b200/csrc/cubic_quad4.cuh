@@ -336,14 +336,20 @@ __device__ __forceinline__ CubicCoef<T> cubic_coef_perm(T u0, T u1, T u2, T u3, 
 
 // A first-level step from its sector: the Horner polynomial, or — `lin`, the point lies outside the grid on dimension 0
 // and linearize_extrapolation is set — y1 + k1*(tt - 1) from the extrapolation slot (fused under the fma feature by the
-// regular-grid struct only: multicubic/regular.rs:553-564 against rectilinear.rs:480-540). `lin_any` is warp-uniform.
-template <bool RECT, class T>
-__device__ __forceinline__ T cubic_coef_eval(const T (&s)[4], T tt, bool lin, bool lin_any) {
+// regular-grid struct only: multicubic/regular.rs:553-564 against rectilinear.rs:480-540). LIN is a compile-time copy of
+// the warp-uniform "some lane of this point group is linearized": the caller branches ONCE per point between the two
+// instantiations of the whole reduction (quad4_reduce) — left as a run-time flag around these three instructions, ptxas
+// predicated them and every sector paid for both formulas and two selects (ncu: 17 of ~75 instructions per four sectors).
+template <bool RECT, bool LIN, class T>
+__device__ __forceinline__ T cubic_coef_eval(const T (&s)[4], T tt, bool lin) {
     using O = Ops<T>;
     const T cub = muladd(muladd(muladd(s[3], tt, s[2]), tt, s[1]), tt, s[0]);
-    if (!lin_any) return cub;
-    const T linv = muladd<!RECT>(s[1], O::sub(tt, T(1)), s[0]);
-    return lin ? linv : cub;
+    if constexpr (!LIN) {
+        return cub;
+    } else {
+        const T linv = muladd<!RECT>(s[1], O::sub(tt, T(1)), s[0]);
+        return lin ? linv : cub;
+    }
 }
 
 // Row (or lane) order of the permuted inputs: interior 0,1,2,3; low end 2,1,0,3; high end 1,2,3,3.
@@ -477,13 +483,13 @@ __device__ __forceinline__ int cubic_perm_k(int mode, int k) {
 #define IB200_QUAD4_UNROLL_OUTER 1  // outermost loop of a 4-D footprint: 1 = rolled (four inner groups of 4 loads), 4 = unrolled
 #endif
 constexpr int kQuad4UnrollOuter = IB200_QUAD4_UNROLL_OUTER;
-template <int D, class T, int N, bool RECT>
+template <int D, bool LIN, class T, int N, bool RECT>
 __device__ __forceinline__ T quad4_reduce(const EvalArgs<T, N>& a, const T* __restrict__ axes, int idx,
-                                          const QuadRef<T, N, RECT>& sp, T tt0, int flags, unsigned none_mask, bool lin_any) {
+                                          const QuadRef<T, N, RECT>& sp, T tt0, int flags, unsigned none_mask) {
     if constexpr (D == 1) {
         T s[4];
         load_row<T, 4, true, int>(nullptr, a.win, idx, s);
-        return cubic_coef_eval<RECT>(s, tt0, (flags & 4) != 0, lin_any);
+        return cubic_coef_eval<RECT, LIN>(s, tt0, (flags & 4) != 0);
     } else {
         const int fl = flags >> (4 * (D - 1));
         const bool all_none = (none_mask >> (D - 1)) & 1u;
@@ -494,14 +500,14 @@ __device__ __forceinline__ T quad4_reduce(const EvalArgs<T, N>& a, const T* __re
             // the four sub-results are shifted through u0..u3 so that no register array is indexed dynamically
 #pragma unroll(kQuad4UnrollOuter)
             for (int k = 0; k < 4; ++k) {
-                const T v = quad4_reduce<D - 1, T, N, RECT>(a, axes, idx + cubic_perm_k(mode, k) * stride, sp, tt0, flags, none_mask, lin_any);
+                const T v = quad4_reduce<D - 1, LIN, T, N, RECT>(a, axes, idx + cubic_perm_k(mode, k) * stride, sp, tt0, flags, none_mask);
                 u0 = u1; u1 = u2; u2 = u3; u3 = v;
             }
         } else {
-            u0 = quad4_reduce<D - 1, T, N, RECT>(a, axes, idx + cubic_perm_k(mode, 0) * stride, sp, tt0, flags, none_mask, lin_any);
-            u1 = quad4_reduce<D - 1, T, N, RECT>(a, axes, idx + cubic_perm_k(mode, 1) * stride, sp, tt0, flags, none_mask, lin_any);
-            u2 = quad4_reduce<D - 1, T, N, RECT>(a, axes, idx + cubic_perm_k(mode, 2) * stride, sp, tt0, flags, none_mask, lin_any);
-            u3 = quad4_reduce<D - 1, T, N, RECT>(a, axes, idx + 3 * stride, sp, tt0, flags, none_mask, lin_any);
+            u0 = quad4_reduce<D - 1, LIN, T, N, RECT>(a, axes, idx + cubic_perm_k(mode, 0) * stride, sp, tt0, flags, none_mask);
+            u1 = quad4_reduce<D - 1, LIN, T, N, RECT>(a, axes, idx + cubic_perm_k(mode, 1) * stride, sp, tt0, flags, none_mask);
+            u2 = quad4_reduce<D - 1, LIN, T, N, RECT>(a, axes, idx + cubic_perm_k(mode, 2) * stride, sp, tt0, flags, none_mask);
+            u3 = quad4_reduce<D - 1, LIN, T, N, RECT>(a, axes, idx + 3 * stride, sp, tt0, flags, none_mask);
         }
         const QuadDim<T, RECT> c = quad4_dim<T, N>(a, axes, sp, D - 1);
         if (all_none) return cubic_step_perm(u0, u1, u2, u3, c, fl, true);  // one warp-uniform branch
@@ -590,8 +596,14 @@ __global__ void __launch_bounds__(kBlock, MINB) cubic_quad4_kernel(const __grid_
             unsigned none_mask = 0;
 #pragma unroll
             for (int d = 1; d < N; ++d) none_mask |= (edges[d] & (0x11111111u << p)) == 0u ? (1u << d) : 0u;
-            const bool lin_any = (edges[0] & (0x11111111u << p)) != 0u;
-            xq[b * 5 + p] = quad4_reduce<N - 1, T, N, RECT>(a, axes, sp.base() + static_cast<int>(b), sp, sp.tt(0), flags, none_mask, lin_any);
+            const bool lin_any = (edges[0] & (0x11111111u << p)) != 0u;  // warp-uniform: one branch per point group
+            // (measured, G points/s with / without the second instantiation: C2 32.5 / 30.7, 4-D rectilinear 6.24 / 6.06, but 4-D
+            // regular 8.18 / 8.50 — at 90 % of the L2 -> L1 rate it only pays for the larger code — which keeps one copy)
+            constexpr bool kSplitLin = N <= 3 || RECT;
+            T v;
+            if (kSplitLin && !lin_any) v = quad4_reduce<N - 1, false, T, N, RECT>(a, axes, sp.base() + static_cast<int>(b), sp, sp.tt(0), flags, none_mask);
+            else v = quad4_reduce<N - 1, true, T, N, RECT>(a, axes, sp.base() + static_cast<int>(b), sp, sp.tt(0), flags, none_mask);
+            xq[b * 5 + p] = v;
         }
         const unsigned long long i_cur = i;
         const bool valid_cur = valid;

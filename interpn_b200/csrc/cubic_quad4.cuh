@@ -521,10 +521,47 @@ __device__ __forceinline__ T quad4_reduce(const EvalArgs<T, N>& a, const T* __re
 // 3-D rectilinear 18.0 against 18.3, 4-D regular 8.76 against 8.51, 4-D rectilinear 5.79 against 6.06 G points/s. The
 // kernels are bound by the L2 -> L1 sector rate (C2, 4-D regular) or by issue + FP64 (rectilinear), not by the load latency
 // of one warp: the other resident warps already cover it.
+// Experiment (round 2, north_star's "TMA or cp.async staged coordinate loads"): IB200_QUAD4_TMA=1 replaces the register
+// prefetch of the next block's coordinates by a per-warp double-buffered bulk-copy pipeline — one elected lane issues N
+// cp.async.bulk (1-D TMA) copies of 32 coordinates into shared memory, completion on an mbarrier with expect_tx; the warp
+// waits on the barrier's phase where it used to wait on the loads' scoreboard. Blocks whose coordinates cannot be copied in
+// bulk (pointers not 16-byte aligned, the ragged last block) take the plain loads. Bit-identical (the GPU parity file passes
+// with this build) and SLOWER everywhere (gpurun_out/r2_tma; profiles/r2_c2_tma_variant_ncu.json): C2 29.7 against 32.5 G
+// points/s, 4-D regular 7.03 against 8.55, 3-D rectilinear 16.0 against 18.4. The coordinates were never the problem — 3 of
+// the 19 load instructions per 32 points, already requested a block ahead — and the detour adds 28 % to the shared-memory
+// wavefronts of a kernel whose binding units are the L1 data pipe and the L2 -> L1 sector rate, plus the barrier traffic.
+// Kept as a compile-time variant (default off) so that the measurement can be repeated.
+#ifndef IB200_QUAD4_TMA
+#define IB200_QUAD4_TMA 0
+#endif
+constexpr bool kQuad4Tma = IB200_QUAD4_TMA != 0;
+template <class T, int N>
+__host__ __device__ constexpr int quad4_tma_warp_bytes() {  // [2 buffers][N][32 coordinates] + two mbarriers
+    return kQuad4Tma ? 2 * N * 32 * static_cast<int>(sizeof(T)) + 16 : 0;
+}
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 constexpr int kQuad4XposeQuad = 20;  // transposition buffer: element (node j, point p) of quad q at q*20 + 5j + p, see the kernel
 template <class T, int N, bool RECT>
 __host__ __device__ constexpr size_t quad4_smem_bytes() {  // beyond the staged axes
-    return static_cast<size_t>(kBlock / 32) * (QuadParams<T, N, RECT>::kBytes + 8 * kQuad4XposeQuad * sizeof(T));
+    return static_cast<size_t>(kBlock / 32) * (QuadParams<T, N, RECT>::kBytes + 8 * kQuad4XposeQuad * sizeof(T) + quad4_tma_warp_bytes<T, N>());
 }
 
 // AXSM: the rectilinear axes blob (axes, bucket tables, cell tables) is staged in shared memory — the loads of the
@@ -566,14 +603,54 @@ __global__ void __launch_bounds__(kBlock, MINB) cubic_quad4_kernel(const __grid_
     // The coordinates of the NEXT block of points are requested after the last gather of the current one has been
     // consumed (its registers are free again), so their DRAM latency overlaps the transposition, the final step
     // and the store instead of stalling the next cell location.
+    // (IB200_QUAD4_TMA) per-warp bulk-copy pipeline of the coordinates: buffers [2][N][32] and two mbarriers
+    T* sx = nullptr;
+    unsigned long long* mbar = nullptr;
+    bool obs_aligned = false, cur_tma = false;
+    unsigned phase0 = 0, phase1 = 0;
+    int buf = 0;
+    auto tma_issue = [&](int bf, unsigned long long first) {  // the warp's 32 coordinates of every dimension, one elected lane
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(mbar + bf, N * 32 * static_cast<unsigned>(sizeof(T)));
+#pragma unroll
+            for (int d = 0; d < N; ++d) bulk_copy_g2s(sx + (bf * N + d) * 32, a.obs[d] + first, 32 * static_cast<unsigned>(sizeof(T)), mbar + bf);
+        }
+    };
+    if constexpr (kQuad4Tma) {
+        unsigned char* tma_base = reinterpret_cast<unsigned char*>(s_xpose + kWarps * 8 * kQuad4XposeQuad) + warp * quad4_tma_warp_bytes<T, N>();
+        sx = reinterpret_cast<T*>(tma_base);
+        mbar = reinterpret_cast<unsigned long long*>(tma_base + 2 * N * 32 * sizeof(T));
+        if (lane == 0) {
+            mbar_init(mbar, 1);
+            mbar_init(mbar + 1, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        unsigned long long bits = 0;
+#pragma unroll
+        for (int d = 0; d < N; ++d) bits |= reinterpret_cast<unsigned long long>(a.obs[d]);
+        obs_aligned = (bits & 15ull) == 0ull;
+        __syncwarp();
+    }
     BlockSchedule sched;
     if (!sched.next(a.work, a.n)) return;
     unsigned long long i = sched.blk * blockDim.x + threadIdx.x;
     bool valid = i < a.n;
     T x[N];
+    if (kQuad4Tma && obs_aligned && (i - lane) + 32 <= a.n) {
+        tma_issue(0, i - lane);
+        cur_tma = true;
+    } else {
 #pragma unroll
-    for (int d = 0; d < N; ++d) x[d] = load_query(a.obs[d] + (valid ? i : a.n - 1));
+        for (int d = 0; d < N; ++d) x[d] = load_query(a.obs[d] + (valid ? i : a.n - 1));
+    }
     for (;;) {
+        if (kQuad4Tma && cur_tma) {  // warp-uniform
+            mbar_wait(mbar + buf, buf ? phase1 : phase0);
+            if (buf) phase1 ^= 1u; else phase0 ^= 1u;
+#pragma unroll
+            for (int d = 0; d < N; ++d) x[d] = sx[(buf * N + d) * 32 + lane];
+        }
         bool ok;
         unsigned edges[N];  // d >= 1: lanes (= points) of the warp in an end cell of dimension d; d = 0: linearized on dimension 0
         {
@@ -611,8 +688,16 @@ __global__ void __launch_bounds__(kBlock, MINB) cubic_quad4_kernel(const __grid_
         if (more) {
             i = sched.blk * blockDim.x + threadIdx.x;
             valid = i < a.n;
+            if (kQuad4Tma && obs_aligned && (i - lane) + 32 <= a.n) {
+                __syncwarp();  // every lane has read its coordinates of the buffer that is refilled now (two iterations ago)
+                buf ^= 1;
+                tma_issue(buf, i - lane);
+                cur_tma = true;
+            } else {
+                cur_tma = false;
 #pragma unroll
-            for (int d = 0; d < N; ++d) x[d] = load_query(a.obs[d] + (valid ? i : a.n - 1));
+                for (int d = 0; d < N; ++d) x[d] = load_query(a.obs[d] + (valid ? i : a.n - 1));
+            }
         }
         // Transposition: lane j holds the partial results of its last-dimension node for points 0..3; the owner of
         // point b needs the four nodes' results of point b, in the permuted order of its saturation class.

@@ -121,7 +121,6 @@ BINDING = {
     "c3_cubic4d_rect64": ("quad128B_ldg256_L2_Gsectors_s", 65.0, "L2 -> L1 32-byte sectors (64 coefficient sectors + coordinates per point)"),
     "c3_linear4d_rect64": ("quad128B_aligned_hbm_Glines_s", 1.0, "random aligned 128-byte lines from HBM (one hypercube block per point)"),
     "c4_linear6d_reg24": ("quad128B_aligned_hbm_Glines_s", 4.0, "random aligned 128-byte lines from HBM (four hypercube blocks per point)"),
-    "c1_linear3d_reg20": ("pair_ldg128_L2_Gloads_s", 4.0, "L1 wavefronts of lone gathers (four row pairs per point)"),
     "c5_nearest2d_reg1024": ("gather8B_random_Gloads_s", 1.0, "L1 wavefronts of lone gathers (one node per point)"),
     "c5_nearest3d_reg128": ("gather8B_random_Gloads_s", 1.0, "L1 wavefronts of lone gathers (one node per point)"),
     "c5_nearest2d_rect1024": ("gather8B_random_Gloads_s", 1.0, "L1 wavefronts of lone gathers (one node per point; the axis search adds shared-memory wavefronts)"),

@@ -159,17 +159,18 @@ int window_width(const DeviceGrid& g) {
         // still fits L1 while the 4-fold one would not (C1's 20^3 grid: 137 vs 120 G points/s)
         const size_t b = g.nvals * static_cast<size_t>(g.elem);
         w = (g.ndims >= 2 && !(g.ndims <= 4 && b > (48u << 10) && b <= (100u << 10))) ? 4 : 2;
-        // N = 4..6 beyond L2: the hypercube layout (kernels.cuh linear_hyper_kernel) — the corners of a cell over the last four
-        // dimensions as one aligned block, a 16-fold copy (C3: 2.1 GB, C4: 24.5 GB) that HBM serves at one line per request;
+        // N = 3..6 beyond L2: the hypercube layout (kernels.cuh linear_hyper_kernel / linear_hyper3_kernel) — the corners of a cell
+        // over the last four (N = 3: all three) dimensions as one aligned block, a 16-fold (8-fold) copy (C3: 2.1 GB, C4: 24.5 GB) that HBM serves at one line per request;
         // 180 GB of HBM is what it is for. INTERPN_B200_HYPER_MIN_KB / _MAX_MB bound it (0 MB turns it off: slab passes or the
         // bin-swept path, launch_linear.cu).
         size_t hyper_min_kb = 80u << 10, hyper_max_mb = 32768;
         if (const char* e = getenv("INTERPN_B200_HYPER_MIN_KB")) hyper_min_kb = static_cast<size_t>(strtoull(e, nullptr, 10));
         if (const char* e = getenv("INTERPN_B200_HYPER_MAX_MB")) hyper_max_mb = static_cast<size_t>(strtoull(e, nullptr, 10));
-        if (g.ndims >= 4 && g.ndims <= 6 && b > (hyper_min_kb << 10) && (b << 4) <= (hyper_max_mb << 20) &&
+        const int hbits = g.ndims == 3 ? 3 : 4;  // N = 3: the whole 2^3 footprint (8-fold copy, read by a lane pair)
+        if (g.ndims >= 3 && g.ndims <= 6 && b > (hyper_min_kb << 10) && (b << hbits) <= (hyper_max_mb << 20) &&
             g.nvals < (size_t(1) << 29)) {  // sector index f*4 + j stays below 2^31
             size_t free_b = 0, total_b = 0;
-            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && (b << 4) <= free_b / 4) return 16;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && (b << hbits) <= free_b / 4) return 1 << hbits;
         }
     }
     // cubic N = 1: rows of four; N = 2..4: the coefficient layout (cubic_quad4.cuh), which on rectilinear axes is built from

@@ -649,6 +649,66 @@ __global__ void __launch_bounds__(kBlock) linear_hyper_kernel(const __grid_const
     }
 }
 
+// N = 3: the block is the whole 2^3 footprint (64 bytes in f64, an 8-fold copy), hwin[f*8 + v] with bit b of v = offset along
+// dimension b, read by a PAIR of lanes (sector s = bit 2 = dimension 2; dimensions 0, 1 inside the sector). A quad handles its
+// four points in two steps of two points; the owner finishes with dimension 2.
+template <class T, bool RECT, bool AXSM>
+__device__ __forceinline__ void linear_hyper3_body(const EvalArgs<T, 3>& a) {
+    using O = Ops<T>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const T* axes = nullptr;
+    size_t axes_bytes = 0;
+    if constexpr (RECT) {
+        axes = stage_axes_as<AXSM, T, 3>(a);
+        if constexpr (AXSM) axes_bytes = (static_cast<size_t>(a.axes_total) * sizeof(T) + 15) / 16 * 16;
+    }
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, j = lane & 3u, quad = lane >> 2;
+    const int qb = static_cast<int>(lane & ~3u);
+    const int sct = static_cast<int>(j & 1u), half = static_cast<int>(j >> 1);
+    T* xq = reinterpret_cast<T*>(smem_raw + axes_bytes) + (warp * 8 + quad) * kHyperXposeQuad;
+    const unsigned long long nblocks = (a.n + blockDim.x - 1) / blockDim.x;
+    for (unsigned long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const unsigned long long i = blk * blockDim.x + threadIdx.x;
+        const bool valid = i < a.n;
+        T xs[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) xs[d] = load_query(a.obs[d] + (valid ? i : a.n - 1));
+        T t[3];
+        int base;
+        const bool ok = linear_locate_any<T, 3, RECT, int, true>(a, axes, xs, t, base);
+        if (!ok) base = 0;  // keep the gather in range; the value is discarded
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int p = 2 * u + half;  // this lane pair's point of the step
+            const int bp = __shfl_sync(0xffffffffu, base, qb + p);
+            const T t0 = __shfl_sync(0xffffffffu, t[0], qb + p), t1 = __shfl_sync(0xffffffffu, t[1], qb + p);
+            T v[4];
+            load_row<T, 4, true, long long>(nullptr, a.win, static_cast<long long>(bp) * 2 + sct, v);
+            const T a0 = muladd(t0, O::sub(v[1], v[0]), v[0]);
+            const T a1 = muladd(t0, O::sub(v[3], v[2]), v[2]);
+            xq[sct * 5 + p] = muladd(t1, O::sub(a1, a0), a0);
+        }
+        __syncwarp();
+        const T w0 = xq[j], w1 = xq[5 + j];  // this lane's point: the results of its two sectors
+        __syncwarp();  // the next iteration overwrites the buffer
+        const T res = muladd(t[2], O::sub(w1, w0), w0);
+        if (valid) {
+            if (ok) store_result(a.out + i, res);
+            else report_bad(a, i);
+        }
+    }
+}
+
+template <class T, bool RECT>
+__global__ void __launch_bounds__(kBlock) linear_hyper3_kernel(const __grid_constant__ EvalArgs<T, 3> a) {
+    if constexpr (RECT) {
+        if (a.axes_in_smem) linear_hyper3_body<T, RECT, true>(a);
+        else linear_hyper3_body<T, RECT, false>(a);
+    } else {
+        linear_hyper3_body<T, RECT, false>(a);
+    }
+}
+
 // Slab passes — multilinear straight from `vals` on a grid a little beyond L2 (C3: 134 MB against 126 MB), whose
 // footprints are too few rows for the bin-swept path to pay. The batch is evaluated in a few launches; each takes only
 // the points whose dimension-0 coordinate lies between two nodes of axis 0, so that all of a launch's gathers fall in

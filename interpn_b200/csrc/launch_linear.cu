@@ -45,6 +45,15 @@ cudaError_t launch_linear_n(const DeviceGrid& g, const T* const* obs, size_t n, 
             return launch_generic<T, N>(linear_hyper_kernel<T, N, RECT>, g, obs, n, out, first_bad, index_base, stream, o);
         }
     }
+    if constexpr (N == 3) {  // 3-D grids beyond L2: one aligned 8-value block per point, read by a lane pair
+        if (g.win != nullptr && g.win_width == 8 && !index64(g)) {
+            LaunchOpts o;
+            o.window = true;
+            o.extra_smem = linear_hyper_smem_bytes<T>();
+            o.ctas_per_sm = static_cast<int>(sweep_env("INTERPN_B200_HYPER_CTAS", 8));
+            return launch_generic<T, 3>(linear_hyper3_kernel<T, RECT>, g, obs, n, out, first_bad, index_base, stream, o);
+        }
+    }
     const bool has_patch = kCanWin && g.win != nullptr && g.win_width == kPatch;
     const bool has_rows = N >= 2 && N <= 4 && g.win != nullptr && g.win_width == 2;
     if constexpr (N >= 2) {  // grids beyond L2: bin-swept evaluation (sweep.cuh), from the patch layout when there is one

@@ -79,19 +79,19 @@ __global__ void __launch_bounds__(kBlock) build_pwindow_kernel(const T* __restri
     }
 }
 
-// Hypercube layout (kernels.cuh linear_hyper_kernel): hwin[f*16 + v] = vals[f + sum_b bit_b(v)*stride_{N-4+b}]; offsets
+// Hypercube layout (kernels.cuh linear_hyper_kernel, linear_hyper3_kernel): hwin[f*2^nbits + v] = vals[f + sum_b bit_b(v)*stride_{N-nbits+b}]
+// (nbits = 4 for N = 4..6, 3 for N = 3); offsets
 // that would leave the grid along a dimension are dropped (never read: a footprint origin is at most dim-2).
 template <class T>
 __global__ void __launch_bounds__(kBlock) build_hwindow_kernel(const T* __restrict__ vals, T* __restrict__ hwin,
-                                                               unsigned long long nvals, const __grid_constant__ HyperDims hd) {
-    const unsigned long long total = nvals << 4;
+                                                               unsigned long long nvals, int nbits, const __grid_constant__ HyperDims hd) {
+    const unsigned long long total = nvals << nbits;
     const unsigned long long gstride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
     for (unsigned long long k = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; k < total; k += gstride) {
-        const unsigned long long f = k >> 4;
-        const unsigned v = static_cast<unsigned>(k) & 15u;
+        const unsigned long long f = k >> nbits;
+        const unsigned v = static_cast<unsigned>(k) & ((1u << nbits) - 1u);
         unsigned long long src = f;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {  // hd holds the last four dimensions
+        for (int b = 0; b < nbits; ++b) {  // hd holds the last `nbits` dimensions
             const unsigned long long id = (f / static_cast<unsigned long long>(hd.stride[b])) % static_cast<unsigned long long>(hd.dim[b]);
             if (((v >> b) & 1u) && id + 1 < static_cast<unsigned long long>(hd.dim[b])) src += static_cast<unsigned long long>(hd.stride[b]);
         }
@@ -101,15 +101,16 @@ __global__ void __launch_bounds__(kBlock) build_hwindow_kernel(const T* __restri
 
 cudaError_t launch_build_window(const DeviceGrid& g, cudaStream_t stream) {
     if (!g.win || g.nvals == 0) return cudaSuccess;
-    if (g.method == 0 && g.ndims >= 4 && g.win_width == 16) {  // INTERPN_B200_LINEAR, hypercube layout
+    if (g.method == 0 && ((g.ndims >= 4 && g.win_width == 16) || (g.ndims == 3 && g.win_width == 8))) {  // INTERPN_B200_LINEAR, hypercube layout
+        const int nbits = g.ndims == 3 ? 3 : 4;
         HyperDims hd{};
-        for (int b = 0; b < 4; ++b) {
-            hd.dim[b] = g.dim[g.ndims - 4 + b];
-            hd.stride[b] = g.stride[g.ndims - 4 + b];
+        for (int b = 0; b < nbits; ++b) {
+            hd.dim[b] = g.dim[g.ndims - nbits + b];
+            hd.stride[b] = g.stride[g.ndims - nbits + b];
         }
-        const unsigned grid_dim = grid_for(g.nvals << 4, g.sm_count, 8);
-        if (g.elem == 8) build_hwindow_kernel<double><<<grid_dim, kBlock, 0, stream>>>(static_cast<const double*>(g.vals), static_cast<double*>(g.win), g.nvals, hd);
-        else build_hwindow_kernel<float><<<grid_dim, kBlock, 0, stream>>>(static_cast<const float*>(g.vals), static_cast<float*>(g.win), g.nvals, hd);
+        const unsigned grid_dim = grid_for(g.nvals << nbits, g.sm_count, 8);
+        if (g.elem == 8) build_hwindow_kernel<double><<<grid_dim, kBlock, 0, stream>>>(static_cast<const double*>(g.vals), static_cast<double*>(g.win), g.nvals, nbits, hd);
+        else build_hwindow_kernel<float><<<grid_dim, kBlock, 0, stream>>>(static_cast<const float*>(g.vals), static_cast<float*>(g.win), g.nvals, nbits, hd);
         count_launch();
         return cudaGetLastError();
     }

@@ -207,15 +207,15 @@ def test_slab_passes_bit_exact(ib, oracle, monkeypatch, ndims, dtype):
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-@pytest.mark.parametrize("ndims", [4, 5, 6])
+@pytest.mark.parametrize("ndims", [3, 4, 5, 6])
 def test_hypercube_layout_bit_exact(ib, oracle, monkeypatch, ndims, dtype):
-    """The hypercube layout of the multilinear kernels (kernels.cuh linear_hyper_kernel: N = 4..6 grids beyond L2, C3-linear and C4)
+    """The hypercube layout of the multilinear kernels (kernels.cuh linear_hyper_kernel / linear_hyper3_kernel: N = 3..6 grids beyond L2, C3-linear and C4)
     forced onto small grids: every cell incl. the last one of each axis, points on nodes, outside the grid, and
     unrepresentable points (regular) / NaN and infinities (rectilinear)."""
     monkeypatch.setenv("INTERPN_B200_HYPER_MIN_KB", "0")
     rng = np.random.default_rng(4471 + ndims)
     n = 200_003
-    lo, hi = {4: (4, 8), 5: (3, 6), 6: (3, 5)}[ndims]
+    lo, hi = {3: (5, 12), 4: (4, 8), 5: (3, 6), 6: (3, 5)}[ndims]
     dims, grids, starts, steps, vals, obs = random_case(rng, ndims, n, lo, hi, dtype)
     for d in range(ndims):  # exact nodes of every axis, the last one among them
         obs[d][d * 64 : d * 64 + 64] = np.resize(grids[d], 64)

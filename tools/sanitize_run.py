@@ -64,7 +64,7 @@ for dtype in (np.float64, np.float32):
     for nd in (3, 4, 5):
         run("linear", nd, dtype, 30_011, SLAB, maxdim={3: 14, 4: 8, 5: 6}[nd])  # warp-compacting slab passes
         cases += 1
-    for nd in (4, 5, 6):
+    for nd in (3, 4, 5, 6):
         run("linear", nd, dtype, 9001, HYPER)  # quad-cooperative hypercube kernels (shared-memory transposition behind __syncwarp)
         cases += 1
     run("linear", 3, dtype, 3001, {"INTERPN_B200_INDEX64": "1"})

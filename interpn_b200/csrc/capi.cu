@@ -148,10 +148,10 @@ int validate_interp(size_t ndims, const size_t* obs_lens, size_t nobs, size_t no
     return INTERPN_B200_OK;
 }
 
-// Which grids get the window layout (kernels.cuh load_row). It multiplies the footprint by W, so it is
-// reserved for grids that are too big for L1 to capture row reuse, yet whose W-fold copy still sits
-// comfortably inside the 126 MB L2 next to the streaming query traffic. INTERPN_B200_WINDOW_MB overrides
-// the upper bound (0 disables the layout).
+// Which derived copy of `vals` a grid gets (interp_internal.h DeviceGrid::win). The patch / coefficient
+// copies multiply the grid by ~4 and pay while that copy sits in L2 (direct kernels) or is swept slab by slab (sweep.cuh);
+// the hypercube copies multiply it by 8 / 16 and serve grids beyond L2 from HBM one line per request.
+// INTERPN_B200_WINDOW_MB / INTERPN_B200_HYPER_MAX_MB bound them (0 disables).
 int window_width(const DeviceGrid& g) {
     int w = 0;
     if (g.method == INTERPN_B200_LINEAR && g.ndims <= 6) {
@@ -160,8 +160,8 @@ int window_width(const DeviceGrid& g) {
         const size_t b = g.nvals * static_cast<size_t>(g.elem);
         w = (g.ndims >= 2 && !(g.ndims <= 4 && b > (48u << 10) && b <= (100u << 10))) ? 4 : 2;
         // N = 3..6 beyond L2: the hypercube layout (kernels.cuh linear_hyper_kernel / linear_hyper3_kernel) — the corners of a cell
-        // over the last four (N = 3: all three) dimensions as one aligned block, a 16-fold (8-fold) copy (C3: 2.1 GB, C4: 24.5 GB) that HBM serves at one line per request;
-        // 180 GB of HBM is what it is for. INTERPN_B200_HYPER_MIN_KB / _MAX_MB bound it (0 MB turns it off: slab passes or the
+        // over the last four (N = 3: all three) dimensions as one aligned block, a 16-fold (8-fold) copy (C3: 2.1 GB, C4: 24.5 GB)
+        // that HBM serves at one line per request; 180 GB of HBM is what it is for. INTERPN_B200_HYPER_MIN_KB / _MAX_MB bound it (0 MB turns it off: slab passes or the
         // bin-swept path, launch_linear.cu).
         size_t hyper_min_kb = 80u << 10, hyper_max_mb = 32768;
         if (const char* e = getenv("INTERPN_B200_HYPER_MIN_KB")) hyper_min_kb = static_cast<size_t>(strtoull(e, nullptr, 10));

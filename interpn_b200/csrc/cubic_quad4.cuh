@@ -14,7 +14,7 @@
 //   slot 0 / dim0 = (y1, k1, 0, 0) of the linearized extrapolation below / above the grid.
 // A first-level step is then ONE sector load and three multiply-adds (6 FP64 instructions; 3 in the fma flavour)
 // instead of four loads and 14 (regular) or 30 (rectilinear) instructions, bit for bit the reference's result. The
-// table is the size of the former four-fold cross-window copy (x (dim0 + 1)/dim0).
+// table is four times the grid (x (dim0 + 1)/dim0), the size of the window copy of round 1 that it replaces.
 //
 // Work split (unchanged from the second generation, profiles/r1_p5_c2_quad4_ncu.json):
 //   * thread i OWNS point i: it loads the point's coordinates (coalesced), locates it on every dimension with the

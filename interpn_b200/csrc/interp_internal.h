@@ -31,8 +31,10 @@ struct DeviceGrid {
     double step[kMaxNd] = {};
     void* vals = nullptr;           // device, nvals elements
     size_t nvals = 0;
-    // Window layout of `vals` (kernels.cuh load_row): win[f*W + j] = vals[min(f + j, nvals-1)], W = 2
-    // (linear) or 4 (cubic). Present only for mid-size grids (window_policy in capi.cu).
+    // Derived copy of `vals` the kernels gather from (policy: capi.cu window_width, builders: launch_misc.cu,
+    // launch_cubic_build.cu). win_width = elements per flat index: 2 row pairs / 4 rows of four (plain), 4 = 2x2 patches
+    // (linear, win_cross) or first-level coefficient sectors (cubic N = 2..4, win_cross), 8 / 16 = hypercube blocks (linear
+    // beyond L2, N = 3 / N = 4..6). nullptr when the grid has none.
     void* win = nullptr;
     int win_width = 0;
     int win_cross = 0;         // not plain rows: linear N >= 2 the 2x2 patch layout, cubic N = 2..4 the coefficient layout

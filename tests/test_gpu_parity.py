@@ -485,16 +485,30 @@ def test_fused_fields_equal_separate_calls(ib, oracle, method, ndims, rect):
         it.close()
 
 
-def test_vals_from_device_and_uninitialised_storage(ib):
+@pytest.mark.parametrize("method,ndims,rect,hyper", [("linear", 3, False, False), ("cubic", 3, False, False), ("cubic", 3, True, False),
+                                                     ("cubic", 4, True, False), ("linear", 4, True, True), ("linear", 3, False, True)])  # fmt: skip
+def test_vals_from_device_and_uninitialised_storage(ib, monkeypatch, method, ndims, rect, hyper):
+    """Values given on the device, and values written into uninitialised resident storage afterwards (the multi-GPU
+    broadcast): `vals_updated` must rebuild whatever derived layout the grid has — patch, coefficient table (regular and
+    rectilinear), hypercube blocks — so all three interpolators agree bit for bit."""
     torch = pytest.importorskip("torch")
-    rng = np.random.default_rng(8)
-    dims = [9, 7, 5]
-    starts, steps = np.zeros(3), np.ones(3)
-    vals = rng.standard_normal(9 * 7 * 5)
-    obs = [rng.random(1000) * 8, rng.random(1000) * 6, rng.random(1000) * 4]
-    a = ib.Interpolator.regular("linear", dims, starts, steps, vals)
-    b = ib.Interpolator.regular("linear", dims, starts, steps, torch.from_numpy(vals).cuda())
-    c = ib.Interpolator.regular("linear", dims, starts, steps, None, dtype=np.float64)
+    if hyper:
+        monkeypatch.setenv("INTERPN_B200_HYPER_MIN_KB", "0")
+    rng = np.random.default_rng(8 + ndims)
+    dims = [9, 7, 5, 6][:ndims]
+    starts, steps = np.zeros(ndims), np.ones(ndims)
+    grids = [np.cumsum(rng.random(d) + 0.2) for d in dims]
+    vals = rng.standard_normal(int(np.prod(dims)))
+    obs = [rng.random(5000) * (g[-1] - g[0]) * 1.2 + g[0] - 0.1 * (g[-1] - g[0]) for g in (grids if rect else [np.arange(d, dtype=float) for d in dims])]
+
+    def make(v, **kw):
+        if rect:
+            return ib.Interpolator.rectilinear(method, grids, v, True, **kw)
+        return ib.Interpolator.regular(method, dims, starts, steps, v, True, **kw)
+
+    a = make(vals)
+    b = make(torch.from_numpy(vals).cuda())
+    c = make(None, dtype=np.float64)
     assert c.vals_len == vals.size and c.vals_ptr != 0
     # fill c's storage the way the multi-GPU broadcast does: through a tensor aliasing the resident copy
     c.vals_tensor().copy_(torch.from_numpy(vals).cuda())
@@ -503,7 +517,14 @@ def test_vals_from_device_and_uninitialised_storage(ib):
     ra, rb, rc = a.eval(obs), b.eval(obs), c.eval(obs)
     assert_same_bits(ra, rb)
     assert_same_bits(ra, rc)
-    for x in (a, b, c):
+    # new values through the same storage: the derived layout must follow
+    vals2 = rng.standard_normal(vals.size)
+    c.vals_tensor().copy_(torch.from_numpy(vals2).cuda())
+    c.vals_updated(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    d = make(vals2)
+    assert_same_bits(c.eval(obs), d.eval(obs))
+    for x in (a, b, c, d):
         x.close()
 
 

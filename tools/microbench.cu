@@ -132,6 +132,26 @@ __global__ void quad_gather_kernel(const double* __restrict__ tab, unsigned nsec
     if (s == 123.456) out[0] = s;
 }
 
+// The same with W consecutive 128-byte lines per quad (aligned to W lines): W loads per lane, chunks of W*128 bytes.
+template <int W>
+__global__ void chunk_gather_kernel(const double* __restrict__ tab, unsigned nsectors, int per, double* out) {
+    unsigned x = ((blockIdx.x * blockDim.x + threadIdx.x) >> 2) * 2654435761u + 12345u;  // quad-uniform stream
+    const unsigned j = threadIdx.x & 3u;
+    double s = 0;
+    for (int i = 0; i < per; i += 8 / W) {
+        D4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8 / W; ++k) {
+            unsigned r = __umulhi(lcg(x), nsectors - 4 * W) & ~(4u * W - 1u);
+#pragma unroll
+            for (int w = 0; w < W; ++w) v[k * W + w] = reinterpret_cast<const D4*>(tab)[r + 4 * w + j];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+    if (s == 123.456) out[0] = s;
+}
+
 // Random shared-memory gathers with cheap indices. W = 1: LDS.64, 2: LDS.128 (16-byte aligned pair).
 template <int W>
 __global__ void smem_gather2_kernel(const double* __restrict__ tab, int n, int per, double* out) {
@@ -262,6 +282,10 @@ int main() {
             float h1 = time_ms([&] { quad_gather_kernel<1><<<blocks, threads>>>(big, unsigned(big_sectors), per, out); });
             float h0 = time_ms([&] { quad_gather_kernel<0><<<blocks, threads>>>(big, unsigned(big_sectors), per, out); });
             printf(", \"quad128B_aligned_hbm_Glines_s\": %.2f, \"quad128B_unaligned_hbm_Gquads_s\": %.2f", rows / 4 / h1 * 1e-6, rows / 4 / h0 * 1e-6);
+            float c1 = time_ms([&] { chunk_gather_kernel<1><<<blocks, threads>>>(big, unsigned(big_sectors), per, out); });
+            float c2 = time_ms([&] { chunk_gather_kernel<2><<<blocks, threads>>>(big, unsigned(big_sectors), per, out); });
+            float c4 = time_ms([&] { chunk_gather_kernel<4><<<blocks, threads>>>(big, unsigned(big_sectors), per, out); });
+            printf(", \"chunk128B_hbm_TBs\": %.3f, \"chunk256B_hbm_TBs\": %.3f, \"chunk512B_hbm_TBs\": %.3f", rows * 32 / c1 * 1e-9, rows * 32 / c2 * 1e-9, rows * 32 / c4 * 1e-9);
             CK(cudaFree(big));
         }
         float q0 = time_ms([&] { quad_gather_kernel<0><<<blocks, threads>>>(tab, n32 / 4, per, out); });

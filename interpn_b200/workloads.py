@@ -250,6 +250,11 @@ def get(name: str, dtype=np.float64) -> Workload:
     if name == "x_cubic4d_reg32":
         return _regular(name, "cubic", [32] * 4, [0.0] * 4, [1.0] * 4, dtype, 100_000_000,
                         linearize=True, oob_fraction=0.10)  # fmt: skip
+    if name == "x_cubic2d_reg1024":
+        return _regular(name, "cubic", [1024] * 2, [0.0] * 2, [0.125] * 2, dtype, 100_000_000,
+                        linearize=True, oob_fraction=0.10)  # fmt: skip
+    if name == "x_cubic2d_rect1024":
+        return _rectilinear(name, "cubic", 2, 1024, dtype, 100_000_000, linearize=True, oob_fraction=0.10)
     if name == "x_cubic3d_rect100":
         return _rectilinear(name, "cubic", 3, 100, dtype, 100_000_000, linearize=True, oob_fraction=0.10)
     if name == "x_cubic4d_rect32":
@@ -267,6 +272,7 @@ def get(name: str, dtype=np.float64) -> Workload:
 
 
 EXTRA = ["x_linear3d_reg100", "x_linear4d_reg32", "x_cubic4d_reg32", "x_cubic3d_rect100", "x_cubic4d_rect32", "x_linear4d_rect32",
+         "x_cubic2d_reg1024", "x_cubic2d_rect1024",
          "x_linear3d_reg256", "x_linear4d_reg64", "x_linear5d_reg26"]
 
 ALL = [

@@ -55,7 +55,7 @@ def main():
         except Exception as e:
             print("skip", path, e)
             continue
-        rec.update(points=pts, source=f"gpurun_out/r2_prof/{os.path.basename(path)} (tools/profile_round.sh)")
+        rec.update(points=pts, source=f"profiles/r2_traffic/{os.path.basename(path)} (ncu metrics pass of tools/profile_round.sh)")
         table[f"{wl}:{dt}"] = rec
         print(wl, dt, pts, "%.3f GB" % (rec["bytes"] / 1e9), "%.3f ms" % rec["device_ms"], rec["launches_per_step"], "launches")
     json.dump(table, open(dst, "w"), indent=1)
